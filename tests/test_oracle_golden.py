@@ -1,0 +1,118 @@
+"""The oracle (oracle/nes_oracle.py) against fixtures produced by the reference's own code
+(oracle/make_golden.py, run where /root/reference exists).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import nes_oracle as orc
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = orc.philox4x32_10(*[np.asarray([c]) for c in ctr], *key)
+        assert tuple(int(g[0]) for g in got) == want
+
+
+def test_noise_is_standard_normal_and_counter_based():
+    eps = orc.noise(seed=42, gen=3, member_offset=0, n_members=64, P=4481)
+    assert eps.shape == (64, 4481)
+    assert abs(eps.mean()) < 0.01 and abs(eps.std() - 1) < 0.01
+    # pure function of (seed, gen, member, j): a shard regenerates exactly its rows
+    sub = orc.noise(seed=42, gen=3, member_offset=17, n_members=5, P=4481)
+    assert np.array_equal(sub, eps[17:22])
+    assert not np.array_equal(orc.noise(42, 4, 0, 1, 4481), eps[:1])
+    assert not np.array_equal(orc.noise(43, 3, 0, 1, 4481), eps[:1])
+    # P not a multiple of 4: prefix property
+    assert np.array_equal(orc.noise(42, 3, 0, 2, 4479), eps[:2, :4479])
+
+
+def test_unit_uniform_edges():
+    u = orc.u32_to_unit_f32(np.asarray([0, 1, 2 ** 31, 2 ** 32 - 1], dtype=np.uint32))
+    assert u.dtype == np.float32
+    assert u[0] == np.float32(2.0 ** -33) and u[-1] == np.float32(1.0)
+    assert np.all(u > 0) and np.all(u <= 1)
+
+
+def test_fitness_shift_matches_reference(golden_dir):
+    g = load(golden_dir, 'fitness_shift.npz')
+    for i in range(6):
+        x, y = g['x%d' % i], g['y%d' % i]
+        assert np.array_equal(orc.fitness_shift(x), y)        # fp64, bit exact
+    # pinned behaviours the reference leaves implicit
+    s = orc.fitness_shift([1, 1, 1, 0])                       # ties -> by index
+    assert np.allclose(s, [-1 / 6, 1 / 6, 1 / 2, -1 / 2])
+    s = orc.fitness_shift(np.arange(5.0))
+    assert s[0] == -0.5 and s[-1] == 0.5 and abs(s.sum()) < 1e-15
+
+
+def test_adam_matches_reference(golden_dir):
+    g = load(golden_dir, 'adam.npz')
+    opt = orc.Adam()
+    for t in range(len(g['g'])):
+        assert np.array_equal(opt.update(g['g'][t]), g['step'][t])
+    assert np.array_equal(opt.m, g['m']) and np.array_equal(opt.v, g['v'])
+    # first step is ~sign(g)
+    first = orc.Adam().update(g['g'][0])
+    assert np.allclose(first, np.sign(g["g"][0]), atol=1e-3)
+
+
+@pytest.mark.parametrize('tag', ['pend', 'b64', 'b256'])
+def test_forward_and_flat_layout_match_reference(golden_dir, tag):
+    g = load(golden_dir, 'forward.npz')
+    d0, H, A, T = (int(v) for v in g[tag + '_dims'])
+    flat = g[tag + '_flat']
+    W1, b1, W2, b2, W3, b3 = orc.unflatten(flat, d0, H, A)
+    for ours, name in ((W1, 'fc1w'), (b1, 'fc1b'), (W2, 'fc2w'), (b2, 'fc2b'), (W3, 'fc3w'), (b3, 'fc3b')):
+        assert np.array_equal(ours, g[tag + '_' + name])
+    act = orc.forward(flat, g[tag + '_obs'], d0, H, A)
+    ref = g[tag + '_act'].astype(np.float64)                  # reference forward is fp32 torch
+    assert np.max(np.abs(act - ref)) <= 2e-6 * max(1.0, np.max(np.abs(ref)))
+
+
+@pytest.mark.parametrize('tag', ['pend', 'b64'])
+def test_member_fitness_matches_reference_evaluator(golden_dir, tag):
+    g = load(golden_dir, 'eval_%s.npz' % tag)
+    d0, H, A, T = (int(v) for v in g['dims'])
+    obs, target = orc.synthetic_tape(T, d0, A)
+    fit = orc.evaluate_population(g['theta'], obs, target, float(g['sigma']), float(g['clip']),
+                                  int(g['seed']), 0, 0, int(g['N']), d0, H, A)
+    assert np.all(g['steps'] == T)
+    ref = g['fitness']
+    assert np.max(np.abs(fit - ref) / np.abs(ref)) < 2e-6     # reference forward is fp32
+    assert np.array_equal(orc.ranks_stable(fit), orc.ranks_stable(ref))
+
+
+@pytest.mark.parametrize('tag', ['pend', 'b64'])
+def test_generations_match_reference_train_verbatim(golden_dir, tag):
+    """natural_es.train() run verbatim for 3 generations vs the oracle's nes_generation chain."""
+    g = load(golden_dir, 'train_%s.npz' % tag)
+    d0, H, A, T = (int(v) for v in g['dims'])
+    N, seed, sigma, lr, wd, clip = int(g['N']), int(g['seed']), float(g['sigma']), float(g['lr']), \
+        float(g['wd']), float(g['clip'])
+    obs, target = orc.synthetic_tape(T, d0, A)
+    theta = g['theta0']
+    opt = orc.Adam()
+    # test() at the top of each loop iteration (natural_es.py:54) = noiseless fitness of theta_g
+    assert abs(orc.tape_fitness(orc.forward(theta, obs, d0, H, A), target, clip) - g['test_rewards'][0]) \
+        < 2e-6 * abs(g['test_rewards'][0])
+    for gen in range(int(g['gens'])):
+        out = orc.nes_generation(theta, opt, obs, target, sigma=sigma, clip=clip, seed=seed, gen=gen, N=N,
+                                 d0=d0, H=H, A=A, weight_decay=wd, learning_rate=lr)
+        ref_g = g['grad_after_wd'][gen]
+        ours_g = out['gradient'] * (1 - wd)
+        assert np.linalg.norm(ours_g - ref_g) <= 1e-9 * np.linalg.norm(ref_g), gen
+        assert np.linalg.norm(out['update'] - g['update'][gen]) <= 1e-6 * np.linalg.norm(g['update'][gen])
+        assert np.max(np.abs(out['theta'] - g['theta'][gen])) <= 1e-6
+        theta = out['theta']
+        rew = orc.tape_fitness(orc.forward(theta, obs, d0, H, A), target, clip)
+        assert abs(rew - g['test_rewards'][gen + 1]) < 5e-6 * abs(g['test_rewards'][gen + 1])
