@@ -1,0 +1,555 @@
+// des_nes_eval, precision DES_FWD_F16 / DES_FWD_F16X3: fused sample + perturb + forward + fitness with the two
+// hidden-layer GEMMs on tcgen05 tensor cores.
+//
+// One persistent CTA per SM walks its members (Worker.run natural_es.py:27-32 per member).  For a member
+// and a tile of 128 observations (M = 128 rows = TMEM lanes), StandardFCNet.forward (model.py:34-39) is
+//
+//   D1 = X  W1'^T            tcgen05.mma kind::f16, A = X  (fp16, resident in TMEM), B = W1' tiles (smem)
+//   H1 = tanh(D1 + b1')      epilogue warps: TMEM -> regs -> tanh -> fp16 -> TMEM (A operand of layer 2)
+//   D2 = H1 W2'^T            tcgen05.mma, A = H1 (TMEM), B = W2' tiles (smem ring)
+//   H2 = tanh(D2 + b2')      epilogue warps, registers only
+//   a  = H2 W3'^T + b3'      A <= 8 outputs: exact fp32 FFMA in the same epilogue pass (no third MMA)
+//   fitness += -|| clip(a) - a* ||^2                                              (utils.py:134-137)
+//
+// W' = fp32(theta + sigma*eps) (natural_es.py:28-30) is never stored in HBM: generator warps regenerate
+// eps from the counter RNG and write fp16 operand tiles straight into the 128B-swizzled K-major layout
+// tcgen05 reads, through a ring of [64 rows x 64 k] slots; biases / W3' go to small fp32 arrays.
+//
+// Precision modes
+//   F16    operands rounded to fp16 (11 significant bits, as TF32), fp32 accumulate, MUFU tanh.approx.
+//   F16X3  every operand split x = hi + lo (fp16 each, ~22 bits); D += A_hi B_hi + A_lo B_hi + A_hi B_lo;
+//          accurate tanh.  ~fp32 accuracy at 3 MMAs per k-step.
+//
+// Warp roles: warp 0 = TMEM allocator + single-thread MMA issuer; warps 1..4*NT = epilogue (warp w owns
+// TMEM lane quadrant w%4 of tile slot (w-1)/4); the remaining 8 warps = weight generators.  All hand-offs
+// are mbarriers (generator -> MMA: slot_full/empty; MMA -> epilogue: acc_full/empty; epilogue -> MMA:
+// h_ready / h_free); accumulators are double buffered in TMEM in chunks of 64 columns.
+//
+// Bounds per member-tile: RNG issue (~20 instr/normal), MUFU (2/normal + 1-2/tanh), tensor
+// (2*128*(d0*H + H*H) flop; x3 in F16X3).  See DESIGN.md for the budget and measured numbers.
+#include "des_common.cuh"
+#include "des_tc.cuh"
+
+namespace des {
+
+using namespace tc;
+
+constexpr int kGenWarps = 8;
+constexpr int kGenThreads = kGenWarps * 32;
+constexpr int kK1 = 32;        // layer-1 K (state_dim zero-padded): 2 k-steps of 16
+constexpr int kNC = 64;        // accumulator chunk: 64 output features = one MMA N
+constexpr int kMaxA = 8;
+
+template <int H, int MODE>
+struct TcCfg {
+    static constexpr bool X3 = (MODE == DES_FWD_F16X3);
+    static constexpr int NCH = H / kNC;                       // output-feature chunks per layer
+    static constexpr int KAT = H / 64;                        // 64-wide k atoms of layer 2
+    static constexpr int XCOLS = X3 ? kK1 : kK1 / 2;          // TMEM columns of X per tile (hi [+ lo])
+    static constexpr int ACOLS = X3 ? H : H / 2;              // TMEM columns of H1 per tile slot
+    static constexpr int SLOT_COLS = ACOLS + 2 * kNC;         // + two accumulator stages
+    static constexpr int SLOT_BYTES = (X3 ? 2 : 1) * 64 * 128;   // one B tile: 64 rows x 128 B (hi [+ lo])
+    static constexpr int SMALL_FLOATS = 2 * H + kMaxA * H + kMaxA;   // b1, b2, W3'^T [H][8], b3[8]
+    // tile slots resident in TMEM at once (each needs SLOT_COLS); X for every tile of the tape is extra
+    static constexpr int NT_MAX = (512 - 4 * XCOLS) / SLOT_COLS >= 2 ? 2 : 1;
+};
+
+struct TcArgs {
+    float *fitness;
+    const float *theta, *obs, *target;
+    const des_state *state;
+    Layout L;
+    int T, n_tiles, nt, n_pass, n_slots;
+    float sigma, clip;
+    uint32_t k0, k1, gen;
+    uint64_t member_offset;
+    int64_t n_local;
+};
+
+// barrier block in shared memory
+struct TcBars {
+    uint64_t slot_full[32], slot_empty[32];
+    uint64_t small_full[2], small_empty[2];
+    uint64_t acc_full[2][2], acc_empty[2][2];
+    uint64_t h_ready[2], h_free[2];
+    uint64_t x_ready;
+    uint32_t tmem_base;
+    float fit_part[16];
+};
+
+// eps for 8 consecutive flat parameters starting at j0 (multiple of 4): two quads.
+__device__ __forceinline__ void perturbed8(float (&w)[8], const float *__restrict__ theta, int j0, float sigma,
+                                           uint32_t member, uint32_t gen, uint32_t k0, uint32_t k1) {
+    const float4 t0 = __ldg(reinterpret_cast<const float4 *>(theta + j0));
+    const float4 t1 = __ldg(reinterpret_cast<const float4 *>(theta + j0 + 4));
+    const float4 z0 = noise_quad((uint32_t)(j0 >> 2), member, gen, kStreamNesEps, k0, k1);
+    const float4 z1 = noise_quad((uint32_t)(j0 >> 2) + 1, member, gen, kStreamNesEps, k0, k1);
+    w[0] = __fmaf_rn(sigma, z0.x, t0.x); w[1] = __fmaf_rn(sigma, z0.y, t0.y);
+    w[2] = __fmaf_rn(sigma, z0.z, t0.z); w[3] = __fmaf_rn(sigma, z0.w, t0.w);
+    w[4] = __fmaf_rn(sigma, z1.x, t1.x); w[5] = __fmaf_rn(sigma, z1.y, t1.y);
+    w[6] = __fmaf_rn(sigma, z1.z, t1.z); w[7] = __fmaf_rn(sigma, z1.w, t1.w);
+}
+
+// one perturbed parameter at arbitrary flat index j (slow path: whole quad per element)
+__device__ __forceinline__ float perturbed1(const float *__restrict__ theta, int j, float sigma, uint32_t member,
+                                            uint32_t gen, uint32_t k0, uint32_t k1) {
+    const float4 z = noise_quad((uint32_t)(j >> 2), member, gen, kStreamNesEps, k0, k1);
+    const int e = j & 3;
+    const float zz = e == 0 ? z.x : (e == 1 ? z.y : (e == 2 ? z.z : z.w));
+    return __fmaf_rn(sigma, zz, __ldg(theta + j));
+}
+
+template <bool X3>
+__device__ __forceinline__ void store_octet(uint8_t *slot, int r, int c8, const float (&w)[8]) {
+    uint4 hi, lo;
+    if (X3) {
+        split_h2(w[0], w[1], hi.x, lo.x); split_h2(w[2], w[3], hi.y, lo.y);
+        split_h2(w[4], w[5], hi.z, lo.z); split_h2(w[6], w[7], hi.w, lo.w);
+    } else {
+        hi.x = pack_h2(w[0], w[1]); hi.y = pack_h2(w[2], w[3]); hi.z = pack_h2(w[4], w[5]); hi.w = pack_h2(w[6], w[7]);
+    }
+    const int off = r * 128 + ((c8 ^ (r & 7)) << 4);          // SWIZZLE_128B
+    *reinterpret_cast<uint4 *>(slot + off) = hi;
+    if (X3) *reinterpret_cast<uint4 *>(slot + 8192 + off) = lo;
+}
+
+template <int H, int MODE>
+__global__ void __launch_bounds__(544, 1) eval_tc_kernel(TcArgs a) {
+    using C = TcCfg<H, MODE>;
+    constexpr bool X3 = C::X3;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *ring = smem;                                                        // n_slots * SLOT_BYTES
+    float *small = reinterpret_cast<float *>(ring + (size_t)a.n_slots * C::SLOT_BYTES);   // [2][SMALL_FLOATS]
+    TcBars *bars = reinterpret_cast<TcBars *>(small + 2 * C::SMALL_FLOATS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NT = a.nt;
+    const int n_epi_warps = 4 * NT;
+    const Layout L = a.L;
+    const uint32_t gen = a.state ? (uint32_t)a.state->generation : a.gen;
+
+    if (warp == 0) {
+        tmem_alloc(smem_u32(&bars->tmem_base), 512);
+        if (lane == 0) {
+            for (int s = 0; s < a.n_slots; ++s) {
+                mbar_init(smem_u32(&bars->slot_full[s]), kGenWarps);
+                mbar_init(smem_u32(&bars->slot_empty[s]), 1);
+            }
+            for (int p = 0; p < 2; ++p) {
+                mbar_init(smem_u32(&bars->small_full[p]), kGenWarps);
+                mbar_init(smem_u32(&bars->small_empty[p]), n_epi_warps);
+                mbar_init(smem_u32(&bars->h_ready[p]), 4);
+                mbar_init(smem_u32(&bars->h_free[p]), 1);
+                for (int st = 0; st < 2; ++st) {
+                    mbar_init(smem_u32(&bars->acc_full[p][st]), 1);
+                    mbar_init(smem_u32(&bars->acc_empty[p][st]), 4);
+                }
+            }
+            mbar_init(smem_u32(&bars->x_ready), n_epi_warps);
+            fence_barrier_init();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    // TMEM map: X tiles at [0, n_tiles*XCOLS); tile slot ts at slot_base(ts): H1 [0,ACOLS), stages at ACOLS + st*64
+    const uint32_t x_cols_total = (uint32_t)(a.n_tiles * C::XCOLS);
+    auto slot_base = [&](int ts) { return tmem + x_cols_total + (uint32_t)(ts * C::SLOT_COLS); };
+
+    const int64_t first = blockIdx.x;
+    const int64_t stride = gridDim.x;
+
+    if (warp == 0) {
+        // =================================== MMA issuer (one thread) ===================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_f16(128, kNC);
+            uint32_t slot_c = 0;                 // ring consume counter
+            uint32_t acc_u[2] = {0, 0};          // accumulator-stage use counters per tile slot
+            uint32_t hv[2] = {0, 0};             // (member, pass) counter per tile slot for h_ready
+            mbar_wait(smem_u32(&bars->x_ready), 0);
+            tc_fence_after();
+            for (int64_t m = first; m < a.n_local; m += stride) {
+                for (int pass = 0; pass < a.n_pass; ++pass) {
+                    // ---- layer 1: D1 chunk nc = X W1'[64nc:64nc+64, :]^T
+                    for (int nc = 0; nc < C::NCH; ++nc) {
+                        const uint32_t s = slot_c % a.n_slots, sph = (slot_c / a.n_slots) & 1;
+                        ++slot_c;
+                        mbar_wait(smem_u32(&bars->slot_full[s]), sph);
+                        tc_fence_after();
+                        const uint32_t bbase = smem_u32(ring + (size_t)s * C::SLOT_BYTES);
+                        for (int ts = 0; ts < NT; ++ts) {
+                            const uint32_t u = acc_u[ts]++, st = u & 1, ph = (u >> 1) & 1;
+                            mbar_wait(smem_u32(&bars->acc_empty[ts][st]), ph ^ 1);
+                            tc_fence_after();
+                            const uint32_t d = slot_base(ts) + C::ACOLS + st * kNC;
+                            const uint32_t xa = tmem + (uint32_t)((pass * NT + ts) * C::XCOLS);
+#pragma unroll
+                            for (int ks = 0; ks < kK1 / 16; ++ks) {
+                                const uint64_t bh = smem_desc_sw128(bbase) + (uint64_t)(ks * 2);
+                                mma_f16_ts(d, xa + ks * 8, bh, idesc, ks > 0);
+                                if (X3) {
+                                    const uint64_t bl = smem_desc_sw128(bbase + 8192) + (uint64_t)(ks * 2);
+                                    mma_f16_ts(d, xa + kK1 / 2 + ks * 8, bh, idesc, 1);    // X_lo * W_hi
+                                    mma_f16_ts(d, xa + ks * 8, bl, idesc, 1);              // X_hi * W_lo
+                                }
+                            }
+                            mma_commit(smem_u32(&bars->acc_full[ts][st]));
+                        }
+                        mma_commit(smem_u32(&bars->slot_empty[s]));
+                    }
+                    // ---- layer 2: D2 chunk nc = H1 W2'[64nc:64nc+64, :]^T, k in atoms of 64
+                    for (int nc = 0; nc < C::NCH; ++nc) {
+                        uint32_t st_[2], d_[2];
+                        for (int ts = 0; ts < NT; ++ts) {
+                            const uint32_t u = acc_u[ts]++, st = u & 1, ph = (u >> 1) & 1;
+                            mbar_wait(smem_u32(&bars->acc_empty[ts][st]), ph ^ 1);
+                            st_[ts] = st;
+                            d_[ts] = slot_base(ts) + C::ACOLS + st * kNC;
+                            if (nc == 0) mbar_wait(smem_u32(&bars->h_ready[ts]), hv[ts] & 1);
+                        }
+                        tc_fence_after();
+                        for (int ka = 0; ka < C::KAT; ++ka) {
+                            const uint32_t s = slot_c % a.n_slots, sph = (slot_c / a.n_slots) & 1;
+                            ++slot_c;
+                            mbar_wait(smem_u32(&bars->slot_full[s]), sph);
+                            tc_fence_after();
+                            const uint32_t bbase = smem_u32(ring + (size_t)s * C::SLOT_BYTES);
+                            for (int ts = 0; ts < NT; ++ts) {
+                                const uint32_t ah = slot_base(ts) + ka * 32;
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    const uint64_t bh = smem_desc_sw128(bbase) + (uint64_t)(ks * 2);
+                                    mma_f16_ts(d_[ts], ah + ks * 8, bh, idesc, (ka | ks) != 0);
+                                    if (X3) {
+                                        const uint64_t bl = smem_desc_sw128(bbase + 8192) + (uint64_t)(ks * 2);
+                                        mma_f16_ts(d_[ts], ah + H / 2 + ks * 8, bh, idesc, 1);   // H1_lo * W_hi
+                                        mma_f16_ts(d_[ts], ah + ks * 8, bl, idesc, 1);           // H1_hi * W_lo
+                                    }
+                                }
+                            }
+                            mma_commit(smem_u32(&bars->slot_empty[s]));
+                        }
+                        for (int ts = 0; ts < NT; ++ts) {
+                            mma_commit(smem_u32(&bars->acc_full[ts][st_[ts]]));
+                            if (nc == C::NCH - 1) {
+                                mma_commit(smem_u32(&bars->h_free[ts]));
+                                ++hv[ts];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp <= n_epi_warps) {
+        // =================================== epilogue warps ============================================
+        const int ts = (warp - 1) >> 2;                               // tile slot
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
+        const int row = (warp & 3) * 32 + lane;                       // observation row inside the tile
+        // --- X -> TMEM once, as fp16 (hi [, lo]) : tile tt is handled by the warps of slot tt % NT
+        for (int tt = ts; tt < a.n_tiles; tt += NT) {
+            const float *orow = a.obs + (int64_t)(tt * 128 + row) * L.d0;
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float x0 = (2 * i < L.d0) ? __ldg(orow + 2 * i) : 0.f;
+                const float x1 = (2 * i + 1 < L.d0) ? __ldg(orow + 2 * i + 1) : 0.f;
+                if (X3) split_h2(x0, x1, hi[i], lo[i]);
+                else hi[i] = pack_h2(x0, x1);
+            }
+            tmem_st16(tmem + lane_off + (uint32_t)(tt * C::XCOLS), hi);
+            if (X3) tmem_st16(tmem + lane_off + (uint32_t)(tt * C::XCOLS + 16), lo);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->x_ready));
+
+        uint32_t acc_u = 0, hv = 0, mi = 0;
+        const uint32_t sbase = slot_base(ts) + lane_off;
+        for (int64_t m = first; m < a.n_local; m += stride, ++mi) {
+            const uint32_t p = mi & 1;
+            const float *sm = small + p * C::SMALL_FLOATS;
+            const float *b1 = sm, *b2 = sm + H, *w3 = sm + 2 * H, *b3 = sm + 2 * H + kMaxA * H;
+            mbar_wait(smem_u32(&bars->small_full[p]), (mi >> 1) & 1);
+            float sq = 0.f;
+            for (int pass = 0; pass < a.n_pass; ++pass) {
+                // ---------------- epilogue 1: H1 = tanh(D1 + b1) -> fp16 -> TMEM A buffer
+                for (int nc = 0; nc < C::NCH; ++nc) {
+                    const uint32_t u = acc_u++, st = u & 1, ph = (u >> 1) & 1;
+                    mbar_wait(smem_u32(&bars->acc_full[ts][st]), ph);
+                    tc_fence_after();
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t v[32];
+                        tmem_ld32(sbase + C::ACOLS + st * kNC + half * 32, v);
+                        tmem_wait_ld();
+                        if (half == 1) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ts][st]));
+                        }
+                        if (nc == 0 && half == 0) {
+                            // the previous (member, pass) must have finished reading H1 before we overwrite it
+                            mbar_wait(smem_u32(&bars->h_free[ts]), (hv & 1) ^ 1);
+                            tc_fence_after();
+                        }
+                        uint32_t hi[16], lo[16];
+                        const float4 *bq = reinterpret_cast<const float4 *>(b1 + nc * kNC + half * 32);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 b = bq[i];
+                            const float x0 = __uint_as_float(v[4 * i]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
+                            const float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
+                            if (X3) {
+                                split_h2(tanh_acc(x0), tanh_acc(x1), hi[2 * i], lo[2 * i]);
+                                split_h2(tanh_acc(x2), tanh_acc(x3), hi[2 * i + 1], lo[2 * i + 1]);
+                            } else {
+                                hi[2 * i] = pack_h2(tanh_fast(x0), tanh_fast(x1));
+                                hi[2 * i + 1] = pack_h2(tanh_fast(x2), tanh_fast(x3));
+                            }
+                        }
+                        tmem_st16(sbase + nc * 32 + half * 16, hi);
+                        if (X3) tmem_st16(sbase + H / 2 + nc * 32 + half * 16, lo);
+                    }
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars->h_ready[ts]));
+                ++hv;
+                // ---------------- epilogue 2+3: H2 = tanh(D2 + b2); a = H2 W3^T + b3 in fp32 registers
+                float act[kMaxA];
+#pragma unroll
+                for (int q = 0; q < kMaxA; ++q) act[q] = 0.f;
+                for (int nc = 0; nc < C::NCH; ++nc) {
+                    const uint32_t u = acc_u++, st = u & 1, ph = (u >> 1) & 1;
+                    mbar_wait(smem_u32(&bars->acc_full[ts][st]), ph);
+                    tc_fence_after();
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t v[32];
+                        tmem_ld32(sbase + C::ACOLS + st * kNC + half * 32, v);
+                        tmem_wait_ld();
+                        if (half == 1) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ts][st]));
+                        }
+                        const int n0 = nc * kNC + half * 32;
+                        const float4 *bq = reinterpret_cast<const float4 *>(b2 + n0);
+#pragma unroll
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            const float4 b = bq[i4];
+                            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int i = 4 * i4 + e;
+                                const float x = __uint_as_float(v[i]) + bb[e];
+                                const float h = X3 ? tanh_acc(x) : tanh_fast(x);
+                                // layer 3 (model.py:38) in fp32: W3' stored transposed [n][8] -> one or two LDS.128
+                                const float4 wa = *reinterpret_cast<const float4 *>(w3 + (n0 + i) * kMaxA);
+                                act[0] = __fmaf_rn(h, wa.x, act[0]);
+                                act[1] = __fmaf_rn(h, wa.y, act[1]);
+                                act[2] = __fmaf_rn(h, wa.z, act[2]);
+                                act[3] = __fmaf_rn(h, wa.w, act[3]);
+                                if (L.A > 4) {
+                                    const float4 wb = *reinterpret_cast<const float4 *>(w3 + (n0 + i) * kMaxA + 4);
+                                    act[4] = __fmaf_rn(h, wb.x, act[4]);
+                                    act[5] = __fmaf_rn(h, wb.y, act[5]);
+                                    act[6] = __fmaf_rn(h, wb.z, act[6]);
+                                    act[7] = __fmaf_rn(h, wb.w, act[7]);
+                                }
+                            }
+                        }
+                    }
+                }
+                const int t = (pass * NT + ts) * 128 + row;
+#pragma unroll
+                for (int q = 0; q < kMaxA; ++q) {
+                    if (q < L.A) {
+                        float v = act[q] + b3[q];
+                        v = fminf(fmaxf(v, -a.clip), a.clip);
+                        const float d = v - __ldg(a.target + (int64_t)t * L.A + q);
+                        sq = __fmaf_rn(d, d, sq);
+                    }
+                }
+            }
+            // ---- member done: reduce squared error over all rows / tile slots (fixed order -> deterministic)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            if (lane == 0) bars->fit_part[warp - 1] = sq;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->small_empty[p]));     // done with this member's b/W3
+            asm volatile("bar.sync 1, %0;" ::"r"(n_epi_warps * 32) : "memory");
+            if (warp == 1 && lane == 0) {
+                double f = 0.0;
+                for (int w = 0; w < n_epi_warps; ++w) f += (double)bars->fit_part[w];
+                a.fitness[m] = (float)(-f);
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(n_epi_warps * 32) : "memory");
+        }
+    } else {
+        // =================================== weight generators =========================================
+        const int gtid = threadIdx.x - (1 + n_epi_warps) * 32;          // 0..255
+        uint32_t slot_p = 0, mi = 0;
+        for (int64_t m = first; m < a.n_local; m += stride, ++mi) {
+            const uint32_t member = (uint32_t)(a.member_offset + (uint64_t)m);
+            // ---- small fp32 arrays: b1 | b2 | W3[8][H] | b3[8]
+            const uint32_t p = mi & 1;
+            float *sm = small + p * C::SMALL_FLOATS;
+            mbar_wait(smem_u32(&bars->small_empty[p]), ((mi >> 1) & 1) ^ 1);
+            for (int i = gtid; i < H / 4; i += kGenThreads) {                // b1, b2: aligned quads
+                const float4 z1 = noise_quad((uint32_t)((L.off_b1 >> 2) + i), member, gen, kStreamNesEps, a.k0, a.k1);
+                const float4 t1 = __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_b1) + i);
+                reinterpret_cast<float4 *>(sm)[i] = make_float4(__fmaf_rn(a.sigma, z1.x, t1.x), __fmaf_rn(a.sigma, z1.y, t1.y),
+                                                                __fmaf_rn(a.sigma, z1.z, t1.z), __fmaf_rn(a.sigma, z1.w, t1.w));
+                const float4 z2 = noise_quad((uint32_t)((L.off_b2 >> 2) + i), member, gen, kStreamNesEps, a.k0, a.k1);
+                const float4 t2 = __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_b2) + i);
+                reinterpret_cast<float4 *>(sm + H)[i] = make_float4(__fmaf_rn(a.sigma, z2.x, t2.x), __fmaf_rn(a.sigma, z2.y, t2.y),
+                                                                    __fmaf_rn(a.sigma, z2.z, t2.z), __fmaf_rn(a.sigma, z2.w, t2.w));
+            }
+            for (int i = gtid; i < L.A * H / 4; i += kGenThreads) {          // W3' rows are H floats: aligned quads
+                const float4 z = noise_quad((uint32_t)((L.off_w3 >> 2) + i), member, gen, kStreamNesEps, a.k0, a.k1);
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_w3) + i);
+                const int q = (4 * i) / H, n = (4 * i) - q * H;               // stored transposed: w3t[n][q]
+                float *dst = sm + 2 * H + n * kMaxA + q;
+                dst[0] = __fmaf_rn(a.sigma, z.x, t.x);
+                dst[kMaxA] = __fmaf_rn(a.sigma, z.y, t.y);
+                dst[2 * kMaxA] = __fmaf_rn(a.sigma, z.z, t.z);
+                dst[3 * kMaxA] = __fmaf_rn(a.sigma, z.w, t.w);
+            }
+            if (mi < 2)                                                       // unused action columns stay zero (finite)
+                for (int i = gtid; i < H * kMaxA; i += kGenThreads)
+                    if ((i & (kMaxA - 1)) >= L.A) sm[2 * H + i] = 0.f;
+            if (gtid < L.A) sm[2 * H + kMaxA * H + gtid] = perturbed1(a.theta, L.off_b3 + gtid, a.sigma, member, gen, a.k0, a.k1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->small_full[p]));
+
+            for (int pass = 0; pass < a.n_pass; ++pass) {
+                // ---- layer-1 tiles: rows [64nc, 64nc+64) of W1', k < d0 (zero padded to 32)
+                for (int nc = 0; nc < C::NCH; ++nc) {
+                    const uint32_t s = slot_p % a.n_slots, sph = (slot_p / a.n_slots) & 1;
+                    ++slot_p;
+                    mbar_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
+                    uint8_t *slot = ring + (size_t)s * C::SLOT_BYTES;
+                    {   // 64 rows x 4 octets = 256 items: one per thread
+                        const int r = gtid >> 2, c8 = gtid & 3;
+                        const int n = nc * 64 + r;
+                        float w[8];
+                        if ((L.d0 & 3) == 0) {                                // row starts are quad aligned
+#pragma unroll
+                            for (int hq = 0; hq < 2; ++hq) {
+                                const int k = c8 * 8 + hq * 4;
+                                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (k < L.d0) {
+                                    const int j = L.off_w1 + n * L.d0 + k;
+                                    const float4 z = noise_quad((uint32_t)(j >> 2), member, gen, kStreamNesEps, a.k0, a.k1);
+                                    const float4 t = __ldg(reinterpret_cast<const float4 *>(a.theta + j));
+                                    v = make_float4(__fmaf_rn(a.sigma, z.x, t.x), __fmaf_rn(a.sigma, z.y, t.y),
+                                                    __fmaf_rn(a.sigma, z.z, t.z), __fmaf_rn(a.sigma, z.w, t.w));
+                                }
+                                w[4 * hq] = v.x; w[4 * hq + 1] = v.y; w[4 * hq + 2] = v.z; w[4 * hq + 3] = v.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const int k = c8 * 8 + e;
+                                w[e] = (k < L.d0) ? perturbed1(a.theta, L.off_w1 + n * L.d0 + k, a.sigma, member, gen, a.k0, a.k1) : 0.f;
+                            }
+                        }
+                        store_octet<X3>(slot, r, c8, w);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bars->slot_full[s]));
+                }
+                // ---- layer-2 tiles: rows [64nc, +64) x k [64ka, +64) of W2'
+                for (int nc = 0; nc < C::NCH; ++nc) {
+                    for (int ka = 0; ka < C::KAT; ++ka) {
+                        const uint32_t s = slot_p % a.n_slots, sph = (slot_p / a.n_slots) & 1;
+                        ++slot_p;
+                        mbar_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
+                        uint8_t *slot = ring + (size_t)s * C::SLOT_BYTES;
+#pragma unroll
+                        for (int it = 0; it < 2; ++it) {                      // 512 octets / 256 threads
+                            const int oct = gtid + it * kGenThreads;
+                            const int r = oct >> 3, c8 = oct & 7;
+                            float w[8];
+                            perturbed8(w, a.theta, L.off_w2 + (nc * 64 + r) * H + ka * 64 + c8 * 8, a.sigma, member, gen,
+                                       a.k0, a.k1);
+                            store_octet<X3>(slot, r, c8, w);
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&bars->slot_full[s]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int H, int MODE>
+static int launch_tc(TcArgs &a, cudaStream_t st) {
+    using C = TcCfg<H, MODE>;
+    a.n_tiles = a.T / 128;
+    a.nt = (C::NT_MAX >= 2 && a.n_tiles % 2 == 0) ? 2 : 1;
+    a.n_pass = a.n_tiles / a.nt;
+    if (a.n_tiles * C::XCOLS + a.nt * C::SLOT_COLS > 512) {
+        set_error("des_nes_eval(tensor): tape_len %d needs %d TMEM columns (> 512) for H=%d", a.T,
+                  a.n_tiles * C::XCOLS + a.nt * C::SLOT_COLS, H);
+        return DES_ERR_UNSUPPORTED;
+    }
+    const size_t fixed = 2 * C::SMALL_FLOATS * sizeof(float) + sizeof(TcBars) + 1024;
+    int n_slots = (int)((227 * 1024 - fixed) / C::SLOT_BYTES);
+    if (n_slots > 32) n_slots = 32;
+    const int per_member = C::NCH + C::NCH * C::KAT;
+    if (n_slots > 2 * per_member) n_slots = 2 * per_member;
+    a.n_slots = n_slots;
+    const size_t smem = (size_t)n_slots * C::SLOT_BYTES + fixed;
+    int dev = 0, sms = 148;
+    DES_CUDA(cudaGetDevice(&dev));
+    DES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    DES_CUDA(cudaFuncSetAttribute(eval_tc_kernel<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = a.n_local < sms ? a.n_local : sms;
+    const int threads = (1 + 4 * a.nt + kGenWarps) * 32;
+    eval_tc_kernel<H, MODE><<<(unsigned)grid, threads, smem, st>>>(a);
+    DES_LAUNCH_CHECK("eval_tc_kernel");
+    return DES_OK;
+}
+
+int eval_tc_launch(float *fitness, const float *theta, const float *obs, const float *target, des_dims dims,
+                   double sigma, double clip, uint64_t seed, uint64_t generation, const des_state *state,
+                   int64_t member_offset, int64_t n_local, int precision, cudaStream_t st) {
+    const int H = dims.hidden;
+    if (!(H == 64 || H == 128 || H == 256) || dims.state_dim > kK1 || dims.action_dim > kMaxA || dims.tape_len % 128 != 0) {
+        set_error("des_nes_eval(tensor): needs hidden in {64,128,256}, state_dim <= %d, action_dim <= %d, tape_len %% 128 == 0 "
+                  "(got d0=%d H=%d A=%d T=%d); use DES_FWD_FP32 for other shapes", kK1, kMaxA, dims.state_dim, H,
+                  dims.action_dim, dims.tape_len);
+        return DES_ERR_UNSUPPORTED;
+    }
+    if (((uintptr_t)theta & 15) != 0) {
+        set_error("des_nes_eval(tensor): theta_dev must be 16-byte aligned");
+        return DES_ERR_INVALID_ARGUMENT;
+    }
+    TcArgs a;
+    a.fitness = fitness; a.theta = theta; a.obs = obs; a.target = target; a.state = state;
+    a.L = Layout(dims.state_dim, H, dims.action_dim);
+    a.T = dims.tape_len;
+    a.sigma = (float)sigma; a.clip = (float)clip;
+    a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32); a.gen = (uint32_t)generation;
+    a.member_offset = (uint64_t)member_offset; a.n_local = n_local;
+    const bool x3 = precision == DES_FWD_F16X3;
+    switch (H) {
+        case 64: return x3 ? launch_tc<64, DES_FWD_F16X3>(a, st) : launch_tc<64, DES_FWD_F16>(a, st);
+        case 128: return x3 ? launch_tc<128, DES_FWD_F16X3>(a, st) : launch_tc<128, DES_FWD_F16>(a, st);
+        default: return x3 ? launch_tc<256, DES_FWD_F16X3>(a, st) : launch_tc<256, DES_FWD_F16>(a, st);
+    }
+}
+
+}  // namespace des

@@ -1,0 +1,174 @@
+"""Per-GPU engine for the NES generation: the host logic around the CUDA kernels.
+
+One process per GPU owns a contiguous shard of the population (the reference's Worker processes,
+natural_es.py:10-32, each evaluate whatever task they pop; here member identity is fixed so noise can
+be regenerated instead of shipped).  Per generation (natural_es.py:62-96):
+
+    eval shard            des_nes_eval             -> fitness_all[off:off+n]   (zero elsewhere)
+    [all-reduce fitness_all]   N floats; sum of zero-padded shards == all-gather, ragged shards allowed
+    centered rank         des_centered_rank        -> shaped[n]   (global ranks of the local members)
+    fitness x noise       des_nes_grad_partial     -> partial[P]
+    [all-reduce partial]       P floats — the one collective BASELINE.json's north_star names
+    (1-wd), Adam, step    des_nes_apply + des_state_advance   (identical on every rank: no broadcast)
+
+`kernels` is the module providing the device ops (default: distributedes_b200.ops -> libdes_b200.so).
+It exists so the world_size>1 host logic can be exercised on CPU with gloo by the test-suite, which
+injects an oracle-backed stand-in; the product never runs without the CUDA library.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(N, world_size, rank):
+    """Contiguous split of N members over world_size ranks; the first N % world_size ranks get one more."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError('bad rank %r / world_size %r' % (rank, world_size))
+    base, rem = divmod(int(N), int(world_size))
+    start = rank * base + min(rank, rem)
+    return start, base + (1 if rank < rem else 0)
+
+
+class NESEngine:
+    def __init__(self, *, state_dim, hidden, action_dim, pop_size, theta0, obs, target, sigma, learning_rate,
+                 weight_decay=0.005, clip=1.0, seed=0, precision='fp32', beta1=0.9, beta2=0.999, epsilon=1e-8,
+                 device=None, process_group=None, kernels=None, use_graph=False):
+        if kernels is None:
+            from . import ops as kernels          # loads libdes_b200.so; raises if it is missing
+        self.k = kernels
+        self.pg = process_group
+        distributed = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(process_group) if distributed else 1
+        self.rank = dist.get_rank(process_group) if distributed else 0
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.d0, self.H, self.A = int(state_dim), int(hidden), int(action_dim)
+        self.N = int(pop_size)
+        if self.N < 2:
+            raise ValueError('pop_size must be >= 2 (fitness_shift divides by N-1, utils.py:146)')
+        self.offset, self.n_local = shard_bounds(self.N, self.world, self.rank)
+        self.sigma, self.lr, self.wd, self.clip = float(sigma), float(learning_rate), float(weight_decay), float(clip)
+        self.beta1, self.beta2, self.epsilon = float(beta1), float(beta2), float(epsilon)
+        self.seed, self.precision = int(seed), precision
+        theta0 = np.ascontiguousarray(theta0, dtype=np.float32).reshape(-1)
+        self.P = self.k.param_count(self.d0, self.H, self.A)
+        if theta0.size != self.P:
+            raise ValueError('theta0 has %d entries, the (%d,%d,%d) MLP needs %d' %
+                             (theta0.size, self.d0, self.H, self.A, self.P))
+        dev = self.device
+        self.theta = torch.from_numpy(theta0.copy()).to(dev)
+        self.adam_m = torch.zeros(self.P, dtype=torch.float64, device=dev)
+        self.adam_v = torch.zeros(self.P, dtype=torch.float64, device=dev)
+        self.fitness_all = torch.zeros(self.N, dtype=torch.float32, device=dev)
+        self.shaped = torch.zeros(max(self.n_local, 1), dtype=torch.float32, device=dev)[:self.n_local]
+        self.partial = torch.zeros(self.P, dtype=torch.float32, device=dev)
+        self.update = torch.zeros(self.P, dtype=torch.float32, device=dev)
+        self.state = self.k.new_state(dev, 0)
+        self.rank_ws = self.k.rank_workspace(self.n_local, dev)
+        self.grad_ws = self.k.grad_workspace(self.n_local, self.P, dev)
+        self.set_tape(obs, target)
+        self.generation_index = 0
+        self._graph = None
+        self._use_graph = bool(use_graph) and self.world == 1 and self.device.type == 'cuda'
+
+    # -- inputs ------------------------------------------------------------------------------------------
+    def set_tape(self, obs, target):
+        obs = torch.as_tensor(obs, dtype=torch.float32)
+        target = torch.as_tensor(target, dtype=torch.float32)
+        if obs.dim() != 2 or obs.shape[1] != self.d0 or target.dim() != 2 or target.shape[1] != self.A \
+                or target.shape[0] != obs.shape[0]:
+            raise ValueError('tape shapes %r / %r do not match (T,%d) / (T,%d)' %
+                             (tuple(obs.shape), tuple(target.shape), self.d0, self.A))
+        if getattr(self, 'obs', None) is not None and self.obs.shape == obs.shape:
+            self.obs.copy_(obs, non_blocking=True)          # keep addresses stable for a captured graph
+            self.target.copy_(target, non_blocking=True)
+        else:
+            self.obs = obs.to(self.device).contiguous()
+            self.target = target.to(self.device).contiguous()
+            self._graph = None
+        self.T = int(obs.shape[0])
+
+    # -- the three phases around the two collectives -------------------------------------------------------
+    def evaluate(self):
+        if self.world > 1:
+            self.fitness_all.zero_()
+        if self.n_local:
+            self.k.nes_eval(self.theta, self.obs, self.target, hidden=self.H, sigma=self.sigma, clip=self.clip,
+                            seed=self.seed, state=self.state, member_offset=self.offset, n_local=self.n_local,
+                            precision=self.precision, out=self.fitness_all[self.offset:self.offset + self.n_local])
+        if self.world > 1:
+            dist.all_reduce(self.fitness_all, group=self.pg)
+        return self.fitness_all
+
+    def rank_and_reduce(self):
+        self.k.centered_rank(self.fitness_all, self.offset, self.n_local, workspace=self.rank_ws, out=self.shaped)
+        self.k.nes_grad_partial(self.shaped, self.P, seed=self.seed, state=self.state, member_offset=self.offset,
+                                workspace=self.grad_ws, out=self.partial)
+        if self.world > 1:
+            dist.all_reduce(self.partial, group=self.pg)
+        return self.partial
+
+    def apply(self):
+        self.k.nes_apply(self.theta, self.adam_m, self.adam_v, self.partial, self.N, self.state, sigma=self.sigma,
+                         learning_rate=self.lr, weight_decay=self.wd, beta1=self.beta1, beta2=self.beta2,
+                         epsilon=self.epsilon, update_out=self.update)
+        self.k.state_advance(self.state, self.beta1, self.beta2)
+
+    def _generation_eager(self):
+        self.evaluate()
+        self.rank_and_reduce()
+        self.apply()
+
+    def generation(self):
+        """One full generation, device-resident; returns nothing (read .fitness_all / .update / .theta)."""
+        if self._use_graph:
+            if self._graph is None:
+                self._capture()
+            self._graph.replay()
+        else:
+            self._generation_eager()
+        self.generation_index += 1
+
+    def _capture(self):
+        """Capture eval -> rank -> grad -> apply -> advance as one CUDA graph.  Generation / Adam counters
+        live in device memory (des_state), so the same graph is replayed every generation."""
+        saved = [t.clone() for t in (self.theta, self.adam_m, self.adam_v, self.state)]
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self._generation_eager()                 # warm-up on the side stream (lazy module loading etc.)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._generation_eager()
+        for t, v in zip((self.theta, self.adam_m, self.adam_v, self.state), saved):
+            t.copy_(v)                                # capture does not execute, the warm-up did: roll it back
+        self._graph = g
+
+    # -- host-buffer entry (the reference-facing call: inputs and results live on the host) ---------------------
+    def generation_host(self, obs_host, target_host, theta_out_host=None, fitness_out_host=None):
+        """H2D tape -> generation -> D2H (theta, fitness).  Pinned host tensors make the copies async;
+        the call returns after the results have landed."""
+        self.set_tape(obs_host, target_host)
+        self.generation()
+        if theta_out_host is not None:
+            theta_out_host.copy_(self.theta, non_blocking=True)
+        if fitness_out_host is not None:
+            fitness_out_host.copy_(self.fitness_all, non_blocking=True)
+        if self.device.type == 'cuda':
+            torch.cuda.current_stream(self.device).synchronize()
+
+    # -- conveniences --------------------------------------------------------------------------------------
+    def noiseless_fitness(self, solution=None):
+        """Return of the tape episode for one flat solution (test(), natural_es.py:101-110)."""
+        theta = self.theta if solution is None else torch.as_tensor(
+            np.ascontiguousarray(solution, dtype=np.float32)).to(self.device)
+        out = self.k.nes_eval(theta, self.obs, self.target, hidden=self.H, sigma=0.0, clip=self.clip, seed=self.seed,
+                              generation=0, member_offset=0, n_local=1, precision='fp32')
+        return float(out[0])
+
+    def theta_numpy(self):
+        return self.theta.detach().cpu().numpy()

@@ -1,0 +1,120 @@
+"""NES master loop with the reference's surface (natural_es.py:10-110): Worker / train() / test().
+
+The reference's train() forks `num_workers` CPU processes that pull member indices from a queue, draw
+eps, roll out, and pipe (eps, fitness, steps) back (natural_es.py:21-32, 62-73).  Here a Worker is "the
+process that owns one GPU and a contiguous shard of the population"; the loop body is
+engine.NESEngine.generation().  Launch one process per GPU (torchrun, or `launch()` below) and call
+train(config) in each; with torch.distributed uninitialised it is a single-GPU run.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .engine import NESEngine
+from .utils import Evaluator, SharedStats, StaticNormalizer, logger
+
+
+class Worker:
+    """natural_es.py:10-32 re-cast: owns the shard [offset, offset+n_local) on one GPU.  run() evaluates the
+    shard for the current generation and returns its fitnesses (the reference's result_q payload minus eps,
+    which is never shipped)."""
+
+    def __init__(self, id, param, state_normalizer, task_q, result_q, stop, config, engine=None):
+        self.id = id
+        self.param = param
+        self.state_normalizer = state_normalizer
+        self.task_q, self.result_q, self.stop = task_q, result_q, stop      # kept for signature parity; unused
+        self.config = config
+        self.engine = engine if engine is not None else build_engine(config, param)
+
+    def run(self):
+        e = self.engine
+        e.evaluate()
+        return e.fitness_all[e.offset:e.offset + e.n_local]
+
+
+def build_engine(config, param=None, **kw):
+    env = config.env_fn()
+    theta0 = config.initial_weight if param is None else np.asarray(param, dtype=np.float32)
+    return NESEngine(state_dim=config.state_dim, hidden=config.hidden_size, action_dim=config.action_dim,
+                     pop_size=config.pop_size, theta0=theta0, obs=env.obs, target=env.target, sigma=config.sigma,
+                     learning_rate=config.learning_rate, weight_decay=config.weight_decay, clip=config.clip,
+                     seed=getattr(config, 'seed', 0), precision=getattr(config, 'precision', 'fp32'),
+                     beta1=config.opt.beta1, beta2=config.opt.beta2, epsilon=config.opt.epsilon, **kw)
+
+
+def train(config, engine=None):
+    """natural_es.py:34-99.  Returns [training_rewards, training_steps, training_timestamps]."""
+    stats = SharedStats(config.state_dim)
+    engine = engine if engine is not None else build_engine(config)
+    worker = Worker(engine.rank, None, StaticNormalizer(config.state_dim), None, None, None, config, engine=engine)
+    steps_per_generation = config.pop_size * config.repetitions * engine.T
+
+    training_rewards, training_steps, training_timestamps = [], [], []
+    initial_time = time.time()
+    total_steps = 0
+    iteration = 0
+    while True:
+        test_mean, test_ste = test(config, None, stats, engine=engine)           # :54
+        elapsed_time = time.time() - initial_time
+        training_rewards.append(test_mean)
+        training_steps.append(total_steps)
+        training_timestamps.append(elapsed_time)
+        if engine.rank == 0:
+            logger.info('Test: total steps %d, %f(%f), elapsed time %d' % (total_steps, test_mean, test_ste, elapsed_time))
+
+        worker.run()                                                           # :62-73 (evaluate + gather)
+        rewards = engine.fitness_all
+        total_steps += steps_per_generation                                    # :75
+        r_mean = float(rewards.mean())
+        r_std = float(rewards.std(unbiased=False))
+        if engine.rank == 0:
+            logger.info('Train: iteration %d, %f(%f)' % (iteration, r_mean, r_std / np.sqrt(config.pop_size)))
+        iteration += 1
+        if config.max_steps and total_steps > config.max_steps:                # :82-84
+            break
+        if getattr(config, 'max_generations', 0) and iteration > config.max_generations:
+            break
+        engine.rank_and_reduce()                                               # :90-92
+        engine.apply()                                                         # :93-96
+        engine.generation_index += 1
+    return [training_rewards, training_steps, training_timestamps]
+
+
+def test(config, solution, stats, engine=None):
+    """natural_es.py:101-110: mean and 'ste' of test_repetitions noiseless episodes of `solution`
+    (None = the engine's current parameters)."""
+    if engine is not None:
+        rewards = [engine.noiseless_fitness(solution) for _ in range(config.test_repetitions)]
+    else:
+        normalizer = StaticNormalizer(config.state_dim)
+        normalizer.offline_stats.load_state_dict(stats.state_dict())
+        evaluator = Evaluator(config, normalizer)
+        evaluator.model.set_weight(solution)
+        rewards = [evaluator.single_run()[0] for _ in range(config.test_repetitions)]
+    return np.mean(rewards), np.std(rewards) / config.test_repetitions
+
+
+def _launch_entry(rank, world_size, config_fn, port, result):
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world_size)
+    try:
+        out = train(config_fn())
+        if rank == 0:
+            result.put(out)
+    finally:
+        dist.destroy_process_group()
+
+
+def launch(config_fn, world_size, port=29533):
+    """Spawn one process per GPU and run train(config_fn()) in each (the reference's `for w in workers:
+    w.start()`, natural_es.py:44-45).  config_fn must be picklable (module-level function)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    result = ctx.SimpleQueue()
+    mp.spawn(_launch_entry, args=(world_size, config_fn, port, result), nprocs=world_size, join=True)
+    return result.get()

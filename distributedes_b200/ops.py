@@ -1,0 +1,203 @@
+"""Thin torch-tensor front ends for the C-ABI kernels (include/des_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the stream; every op below passes raw
+pointers to libdes_b200.so, which enqueues hand-written sm_100a kernels on the current stream.
+CPU tensors are an error (there is no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import Dims, Opt, PRECISIONS, State
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, dtype, name, allow_none=False):
+    if t is None:
+        if allow_none:
+            return C.c_void_p(0)
+        raise RuntimeError('%s is None' % name)
+    if not isinstance(t, torch.Tensor):
+        raise RuntimeError('%s must be a torch.Tensor' % name)
+    if not t.is_cuda:
+        raise RuntimeError('%s is a CPU tensor: distributedes_b200 has no CPU path' % name)
+    if t.dtype != dtype:
+        raise RuntimeError('%s must be %s, got %s' % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise RuntimeError('%s must be contiguous' % name)
+    return C.c_void_p(t.data_ptr())
+
+
+def _on(t, name):
+    """Device guard for the tensor that selects the GPU; CPU tensors are an error, not a fallback."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError('%s is a CPU tensor: distributedes_b200 has no CPU path' % name)
+    return torch.cuda.device(t.device)
+
+
+def _precision(p):
+    if isinstance(p, str):
+        if p not in PRECISIONS:
+            raise RuntimeError('unknown precision %r (choose from %s)' % (p, sorted(PRECISIONS)))
+        return PRECISIONS[p]
+    return int(p)
+
+
+def param_count(state_dim, hidden, action_dim):
+    n = _lib.load().des_param_count(state_dim, hidden, action_dim)
+    if n < 0:
+        raise RuntimeError('invalid MLP dims (%r, %r, %r)' % (state_dim, hidden, action_dim))
+    return int(n)
+
+
+def new_state(device, generation=0):
+    """Device-resident des_state {generation, adam_t, beta1_t, beta2_t} as a 32-byte tensor."""
+    st = torch.empty(C.sizeof(State), dtype=torch.uint8, device=device)
+    with torch.cuda.device(st.device):
+        _lib.check(_lib.load().des_state_init(C.c_void_p(st.data_ptr()), generation, _stream()), 'des_state_init')
+    return st
+
+
+def state_advance(state, beta1=0.9, beta2=0.999):
+    with torch.cuda.device(state.device):
+        _lib.check(_lib.load().des_state_advance(_ptr(state, torch.uint8, 'state'), beta1, beta2, _stream()),
+                   'des_state_advance')
+
+
+def read_state(state):
+    raw = bytes(state.cpu().numpy().tobytes())
+    s = State.from_buffer_copy(raw)
+    return dict(generation=s.generation, adam_t=s.adam_t, beta1_t=s.beta1_t, beta2_t=s.beta2_t)
+
+
+def noise_fill(n_members, P, seed, generation, member_offset=0, stream_tag=0, device='cuda'):
+    """eps[n_members, P] fp32 — debug/parity op (natural_es.py:29)."""
+    out = torch.empty((n_members, P), dtype=torch.float32, device=device)
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.load().des_noise_fill(_ptr(out, torch.float32, 'out'), n_members, P, seed, generation,
+                                              member_offset, stream_tag, _stream()), 'des_noise_fill')
+    return out
+
+
+def nes_perturb(theta, n_members, sigma, seed, generation, member_offset=0):
+    """theta'[n_members, P] = fp32(theta + sigma*eps) — debug/parity op (natural_es.py:28-30)."""
+    P = theta.numel()
+    out = torch.empty((n_members, P), dtype=torch.float32, device=theta.device)
+    with _on(theta, 'theta'):
+        _lib.check(_lib.load().des_nes_perturb(_ptr(out, torch.float32, 'out'), _ptr(theta, torch.float32, 'theta'),
+                                               n_members, P, sigma, seed, generation, member_offset, _stream()),
+                   'des_nes_perturb')
+    return out
+
+
+def nes_eval(theta, obs, target, *, hidden, sigma, clip, seed, generation=0, state=None, member_offset=0,
+             n_local, precision='fp32', out=None):
+    """Fused sample+forward+fitness for members [member_offset, member_offset+n_local) -> fitness[n_local]."""
+    T, d0 = obs.shape
+    A = target.shape[1]
+    if target.shape[0] != T:
+        raise RuntimeError('obs has %d rows but target has %d' % (T, target.shape[0]))
+    if theta.numel() != param_count(d0, hidden, A):
+        raise RuntimeError('theta has %d entries, the (%d,%d,%d) MLP needs %d' %
+                           (theta.numel(), d0, hidden, A, param_count(d0, hidden, A)))
+    if out is None:
+        out = torch.empty(n_local, dtype=torch.float32, device=theta.device)
+    elif out.numel() != n_local:
+        raise RuntimeError('out has %d entries, need n_local=%d' % (out.numel(), n_local))
+    with _on(theta, 'theta'):
+        _lib.check(_lib.load().des_nes_eval(
+            _ptr(out, torch.float32, 'out'), _ptr(theta, torch.float32, 'theta'), _ptr(obs, torch.float32, 'obs'),
+            _ptr(target, torch.float32, 'target'), Dims(d0, hidden, A, T), sigma, clip, seed, generation,
+            _ptr(state, torch.uint8, 'state', allow_none=True), member_offset, n_local, _precision(precision),
+            _stream()), 'des_nes_eval')
+    return out
+
+
+def rank_workspace(n_local, device):
+    nbytes = _lib.load().des_rank_workspace_bytes(n_local)
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def centered_rank(fitness_all, member_offset=0, n_local=None, *, workspace=None, return_ranks=False, out=None):
+    """fitness_shift (utils.py:142-148) for a shard of the global fitness vector."""
+    _on(fitness_all, 'fitness_all')
+    N = fitness_all.numel()
+    if n_local is None:
+        n_local = N - member_offset
+    dev = fitness_all.device
+    if out is None:
+        out = torch.empty(n_local, dtype=torch.float32, device=dev)
+    ranks = torch.empty(n_local, dtype=torch.int32, device=dev) if return_ranks else None
+    if workspace is None:
+        workspace = rank_workspace(n_local, dev)
+    with _on(fitness_all, 'fitness_all'):
+        _lib.check(_lib.load().des_centered_rank(
+            _ptr(out, torch.float32, 'out'), _ptr(ranks, torch.int32, 'ranks', allow_none=True),
+            _ptr(fitness_all, torch.float32, 'fitness_all'), N, member_offset, n_local,
+            _ptr(workspace, torch.uint8, 'workspace'), workspace.numel(), _stream()), 'des_centered_rank')
+    return (out, ranks) if return_ranks else out
+
+
+def grad_workspace(n_local, P, device):
+    nbytes = _lib.load().des_grad_workspace_bytes(n_local, P)
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def nes_grad_partial(shaped_local, P, *, seed, generation=0, state=None, member_offset=0, workspace=None, out=None):
+    """partial[P] = sum_i shaped[i] * eps[member_offset+i] (natural_es.py:91, per shard; eps regenerated)."""
+    _on(shaped_local, 'shaped_local')
+    n_local = shaped_local.numel()
+    dev = shaped_local.device
+    if out is None:
+        out = torch.empty(P, dtype=torch.float32, device=dev)
+    if workspace is None:
+        workspace = grad_workspace(n_local, P, dev)
+    with _on(shaped_local, 'shaped_local'):
+        _lib.check(_lib.load().des_nes_grad_partial(
+            _ptr(out, torch.float32, 'out'), _ptr(shaped_local, torch.float32, 'shaped_local'), n_local, P, seed,
+            generation, _ptr(state, torch.uint8, 'state', allow_none=True), member_offset,
+            _ptr(workspace, torch.uint8, 'workspace'), workspace.numel(), _stream()), 'des_nes_grad_partial')
+    return out
+
+
+def nes_apply(theta, adam_m, adam_v, partial_sum, N, state, *, sigma, learning_rate, weight_decay=0.005,
+              beta1=0.9, beta2=0.999, epsilon=1e-8, update_out=None, grad_out=None):
+    """natural_es.py:92-96 + utils.py:159-166, in place on theta / adam_m / adam_v (fp64 Adam state)."""
+    P = theta.numel()
+    with _on(theta, 'theta'):
+        _lib.check(_lib.load().des_nes_apply(
+            _ptr(theta, torch.float32, 'theta'), _ptr(adam_m, torch.float64, 'adam_m'),
+            _ptr(adam_v, torch.float64, 'adam_v'), _ptr(update_out, torch.float32, 'update_out', allow_none=True),
+            _ptr(grad_out, torch.float64, 'grad_out', allow_none=True),
+            _ptr(partial_sum, torch.float32, 'partial_sum'), P, N,
+            Opt(sigma, learning_rate, weight_decay, beta1, beta2, epsilon), _ptr(state, torch.uint8, 'state'),
+            _stream()), 'des_nes_apply')
+
+
+def cma_rank_mu(Y, w, out=None):
+    """dC[n,n] = sum_i w_i y_i y_i^T for Y[lambda_local, n] (rank-mu term of es.tell, cma_es.py:90)."""
+    lam, n = Y.shape
+    if w.numel() != lam:
+        raise RuntimeError('w has %d entries, Y has %d rows' % (w.numel(), lam))
+    if out is None:
+        out = torch.empty((n, n), dtype=torch.float32, device=Y.device)
+    with _on(Y, 'Y'):
+        _lib.check(_lib.load().des_cma_rank_mu(_ptr(out, torch.float32, 'out'), _ptr(Y, torch.float32, 'Y'),
+                                               _ptr(w, torch.float32, 'w'), lam, n, _stream()), 'des_cma_rank_mu')
+    return out
+
+
+def cma_cov_apply(Cmat, dC, pc, *, decay, c1, cmu):
+    """C <- decay*C + c1*pc pc^T + cmu*dC, in place."""
+    n = Cmat.shape[0]
+    with _on(Cmat, 'C'):
+        _lib.check(_lib.load().des_cma_cov_apply(_ptr(Cmat, torch.float32, 'C'), _ptr(dC, torch.float32, 'dC'),
+                                                 _ptr(pc, torch.float32, 'pc', allow_none=True), n, decay, c1, cmu,
+                                                 _stream()), 'des_cma_cov_apply')
+    return Cmat
