@@ -1,0 +1,72 @@
+"""Oracle-backed stand-in for distributedes_b200.ops on CPU tensors.  TEST-ONLY: lets the world_size>1 host
+logic of engine.NESEngine (sharding, the two all-reduces, ragged shards) run under gloo without a GPU.  It has
+the same function names/arguments as the ops module and keeps the des_state counters in a small tensor."""
+import numpy as np
+import torch
+
+from oracle import nes_oracle as orc
+
+
+def param_count(d0, H, A):
+    return orc.param_count(d0, H, A)
+
+
+def new_state(device, generation=0):
+    return torch.tensor([generation, 0, 1.0, 1.0], dtype=torch.float64)     # generation, adam_t, beta1_t, beta2_t
+
+
+def state_advance(state, beta1=0.9, beta2=0.999):
+    state[0] += 1
+    state[1] += 1
+    state[2] *= beta1
+    state[3] *= beta2
+
+
+def rank_workspace(n_local, device):
+    return torch.empty(0)
+
+
+def grad_workspace(n_local, P, device):
+    return torch.empty(0)
+
+
+def nes_eval(theta, obs, target, *, hidden, sigma, clip, seed, generation=0, state=None, member_offset=0, n_local,
+             precision='fp32', out=None):
+    gen = int(state[0]) if state is not None else generation
+    T, d0 = obs.shape
+    A = target.shape[1]
+    f = orc.evaluate_population(theta.numpy(), obs.numpy(), target.numpy(), sigma, clip, seed, gen, member_offset,
+                                n_local, d0, hidden, A)
+    res = torch.from_numpy(f.astype(np.float32))
+    if out is None:
+        return res
+    out.copy_(res)
+    return out
+
+
+def centered_rank(fitness_all, member_offset=0, n_local=None, *, workspace=None, return_ranks=False, out=None):
+    s = orc.fitness_shift(fitness_all.numpy())[member_offset:member_offset + n_local].astype(np.float32)
+    out.copy_(torch.from_numpy(s))
+    return out
+
+
+def nes_grad_partial(shaped_local, P, *, seed, generation=0, state=None, member_offset=0, workspace=None, out=None):
+    gen = int(state[0]) if state is not None else generation
+    n = shaped_local.numel()
+    part = shaped_local.numpy().astype(np.float64) @ orc.noise(seed, gen, member_offset, n, P) if n else np.zeros(P)
+    out.copy_(torch.from_numpy(part.astype(np.float32)))
+    return out
+
+
+def nes_apply(theta, adam_m, adam_v, partial_sum, N, state, *, sigma, learning_rate, weight_decay=0.005, beta1=0.9,
+              beta2=0.999, epsilon=1e-8, update_out=None, grad_out=None):
+    opt = orc.Adam(beta1, beta2, epsilon)
+    opt.m, opt.v = adam_m.numpy().copy(), adam_v.numpy().copy()
+    opt.beta1_t, opt.beta2_t = float(state[2]), float(state[3])
+    g = partial_sum.numpy().astype(np.float64) / N / sigma
+    th, upd = orc.nes_update(theta.numpy(), g, opt, weight_decay, learning_rate)
+    theta.copy_(torch.from_numpy(th))
+    adam_m.copy_(torch.from_numpy(np.asarray(opt.m)))
+    adam_v.copy_(torch.from_numpy(np.asarray(opt.v)))
+    if update_out is not None:
+        update_out.copy_(torch.from_numpy(upd))

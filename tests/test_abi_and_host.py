@@ -1,0 +1,148 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/des_b200.h declares, the ctypes
+signature table covers the header, argument validation happens before any CUDA work, host helpers."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(REPO, 'include', 'des_b200.h')
+
+
+def header_symbols():
+    txt = open(HEADER).read()
+    return sorted(set(re.findall(r'DES_API\s+[\w\s\*]+?\b(des_\w+)\s*\(', txt)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from distributedes_b200 import _lib, build
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build_library()
+    return _lib.load()
+
+
+def test_header_declares_the_expected_surface():
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for must in ['des_nes_eval', 'des_centered_rank', 'des_nes_grad_partial', 'des_nes_apply', 'des_cma_rank_mu',
+                 'des_cma_cov_apply', 'des_noise_fill', 'des_session_generation_host', 'des_last_error']:
+        assert must in syms
+
+
+def test_library_exports_every_header_symbol(lib):
+    from distributedes_b200 import _lib
+    out = subprocess.run(['nm', '-D', '--defined-only', _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r' T (des_\w+)', out))
+    missing = [s for s in header_symbols() if s not in exported]
+    assert not missing, missing
+    # and nothing but the C ABI leaks out of the shared object
+    assert all(s.startswith('des_') for s in re.findall(r' T (\w+)', out))
+
+
+def test_ctypes_table_matches_header(lib):
+    from distributedes_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == header_symbols()
+
+
+def test_struct_layouts_match_header(lib):
+    import ctypes as C
+    from distributedes_b200 import _lib
+    assert C.sizeof(_lib.Dims) == 16 and C.sizeof(_lib.Opt) == 48 and C.sizeof(_lib.State) == 32
+
+
+def test_pure_functions_without_gpu(lib):
+    assert lib.des_param_count(3, 64, 1) == 4481          # SURVEY table, confirmed on StandardFCNet(3,1,64)
+    assert lib.des_param_count(24, 64, 4) == 6020
+    assert lib.des_param_count(24, 256, 4) == 73220
+    assert lib.des_param_count(0, 64, 1) < 0
+    assert lib.des_rank_workspace_bytes(1000) == 4000
+    assert lib.des_grad_workspace_bytes(0, 10) == 0
+    assert lib.des_grad_workspace_bytes(4096, 6020) >= 6020 * 4
+    assert b'sm_100a' in lib.des_version()
+
+
+def test_argument_validation_precedes_cuda(lib):
+    """Bad arguments are rejected with DES_ERR_INVALID_ARGUMENT and a message, with no GPU present."""
+    import ctypes as C
+    from distributedes_b200 import _lib
+    rc = lib.des_centered_rank(None, None, None, 1, 0, 1, None, 0, None)
+    assert rc == -1 and b'N >= 2' in lib.des_last_error()
+    rc = lib.des_nes_eval(None, None, None, None, _lib.Dims(0, 64, 1, 8), 0.1, 1.0, 0, 0, None, 0, 1, 0, None)
+    assert rc == -1 and b'bad dims' in lib.des_last_error()
+    rc = lib.des_nes_eval(None, None, None, None, _lib.Dims(3, 64, 1, 8), 0.1, 1.0, 0, 0, None, 0, 1, 0, None)
+    assert rc == -1 and b'NULL' in lib.des_last_error()
+    rc = lib.des_nes_grad_partial(None, None, 4, 10, 0, 0, None, 0, None, 0, None)
+    assert rc == -1
+    sess = C.c_void_p()
+    theta = (C.c_float * 4481)()
+    rc = lib.des_session_create(C.byref(sess), 0, _lib.Dims(3, 64, 1, 8), 1, 0, 1, _lib.Opt(0.1, 0.1, 0.005, 0.9, 0.999, 1e-8),
+                                2.0, 0, 0, theta)
+    assert rc == -1 and b'population split' in lib.des_last_error()
+    with pytest.raises(RuntimeError, match='status -1'):
+        _lib.check(rc, 'des_session_create')
+
+
+def test_no_cuda_device_is_an_error_not_a_fallback(lib):
+    import ctypes as C
+    import torch
+    from distributedes_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip('this check is for the GPU-less container')
+    assert lib.des_device_count() == 0
+    sess = C.c_void_p()
+    theta = (C.c_float * 4481)()
+    rc = lib.des_session_create(C.byref(sess), 0, _lib.Dims(3, 64, 1, 8), 16, 0, 16,
+                                _lib.Opt(0.1, 0.1, 0.005, 0.9, 0.999, 1e-8), 2.0, 0, 0, theta)
+    assert rc == -3 and b'no CPU fallback' in lib.des_last_error()
+    from distributedes_b200 import ops
+    with pytest.raises(RuntimeError, match='CPU tensor'):
+        ops.centered_rank(torch.zeros(4))
+    from distributedes_b200.utils import fitness_shift
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        fitness_shift([1.0, 2.0])
+
+
+def test_host_model_codec_matches_reference_layout(golden_dir):
+    """model.py get_weight/set_weight: flat layout pinned by the reference's named parameters."""
+    from distributedes_b200.model import StandardFCNet, param_count
+    g = np.load(os.path.join(golden_dir, 'forward.npz'))
+    for tag in ('pend', 'b64', 'b256'):
+        d0, H, A, _ = (int(v) for v in g[tag + '_dims'])
+        net = StandardFCNet(d0, A, H)
+        assert net.get_weight().size == param_count(d0, H, A)
+        net.set_weight(g[tag + '_flat'].astype(np.float64))
+        assert net.get_weight().dtype == np.float32 and np.array_equal(net.get_weight(), g[tag + '_flat'])
+        for ours, name in zip(net.parameters(), ('fc1w', 'fc1b', 'fc2w', 'fc2b', 'fc3w', 'fc3b')):
+            assert np.array_equal(ours, g[tag + '_' + name])
+        with pytest.raises(AssertionError):
+            net.set_weight(np.zeros(3))
+
+
+def test_shard_bounds_cover_population():
+    from distributedes_b200.engine import shard_bounds
+    for N in (2, 7, 16, 4096, 65536, 65537):
+        for G in (1, 2, 3, 8):
+            spans = [shard_bounds(N, G, r) for r in range(G)]
+            assert spans[0][0] == 0 and sum(n for _, n in spans) == N
+            for (s0, n0), (s1, _) in zip(spans, spans[1:]):
+                assert s0 + n0 == s1
+            assert max(n for _, n in spans) - min(n for _, n in spans) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(10, 2, 2)
+
+
+def test_config_surface_matches_reference_attributes():
+    from distributedes_b200.config import BipedalWalkerConfig, PendulumConfig
+    c = PendulumConfig(64)
+    for attr in ['task', 'env_fn', 'repetitions', 'test_repetitions', 'action_dim', 'state_dim', 'hidden_size',
+                 'model_fn', 'initial_weight', 'reward_to_fitness', 'pop_size', 'num_workers', 'max_steps', 'opt',
+                 'weight_decay', 'action_noise_std', 'tag', 'action_clip', 'target', 'sigma', 'learning_rate']:
+        assert hasattr(c, attr), attr
+    assert (c.state_dim, c.action_dim, len(c.initial_weight)) == (3, 1, 4481)
+    assert c.pop_size == 30 and c.weight_decay == 0.005 and c.opt.beta1 == 0.9       # config.py:18-22
+    assert np.array_equal(c.action_clip(np.asarray([-3.0, 0.5, 3.0])), [-2.0, 0.5, 2.0])   # config.py:29
+    b = BipedalWalkerConfig(64)
+    assert (b.state_dim, b.action_dim, len(b.initial_weight)) == (24, 4, 6020)
