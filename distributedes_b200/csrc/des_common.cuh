@@ -56,22 +56,38 @@ constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
 constexpr uint32_t kStreamNesEps = 0u;
 constexpr uint32_t kStreamCmaZ = 1u;
 
+// Round keys k + r*W precomputed on the host (kernel-parameter constant bank): the xor takes them as
+// constant operands, so the key schedule costs no instructions.
+struct PhiloxKey {
+    uint32_t k0[10], k1[10];
+};
+__host__ inline PhiloxKey make_philox_key(uint64_t seed) {
+    PhiloxKey k;
+    for (int r = 0; r < 10; ++r) {
+        k.k0[r] = (uint32_t)seed + (uint32_t)r * kPhiloxW0;
+        k.k1[r] = (uint32_t)(seed >> 32) + (uint32_t)r * kPhiloxW1;
+    }
+    return k;
+}
+
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               uint32_t k0, uint32_t k1) {
+                                               const PhiloxKey &key) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint32_t hi0 = __umulhi(kPhiloxM0, c0), lo0 = kPhiloxM0 * c0;
         const uint32_t hi1 = __umulhi(kPhiloxM1, c2), lo1 = kPhiloxM1 * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ (k0 + (uint32_t)r * kPhiloxW0);
-        const uint32_t n2 = hi0 ^ c3 ^ (k1 + (uint32_t)r * kPhiloxW1);
+        const uint32_t n0 = hi1 ^ c1 ^ key.k0[r];
+        const uint32_t n2 = hi0 ^ c3 ^ key.k1[r];
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
     }
     return make_uint4(c0, c1, c2, c3);
 }
 
-// uint32 -> fp32 uniform in (0, 1]: one fused rounding of float(x)*2^-32 + 2^-33.
-__device__ __forceinline__ float u32_to_unit(uint32_t x) {
-    return __fmaf_rn(__uint2float_rn(x), 0x1p-32f, 0x1p-33f);
+// uint32 -> f = 1 + k*2^-23 in [1,2) from the LOW 23 bits k of the word: one LOP3, no int->float conversion
+// (I2F issues on the 16-lane XU pipe that the Box-Muller MUFUs already load).  The uniform is
+// u = f - (1 - 2^-24) = (2k+1)*2^-24, on the open interval (0,1).
+__device__ __forceinline__ float u32_to_one_two(uint32_t x) {
+    return __uint_as_float(0x3F800000u | (x & 0x007FFFFFu));
 }
 
 __device__ __forceinline__ float lg2_approx(float x) {
@@ -95,23 +111,27 @@ __device__ __forceinline__ float cos_approx(float x) {
     return y;
 }
 
-// Box-Muller: (z0, z1) = sqrt(-2 ln u1) * (cos 2*pi*u2, sin 2*pi*u2).
-// The angle is shifted into (-pi, pi] where the MUFU sin/cos error bound (2^-21.4 abs) holds:
-// cos(2*pi*u) = -cos(2*pi*u - pi), sin likewise, so the sign is folded into r.
+constexpr float kTwoPiF = 6.283185307179586f;             // fl32(2*pi)
+constexpr float kAngOffF = 9.424777586262351f;            // fl32(3*pi - pi*2^-23)
+
+// Box-Muller.  With f1, f2 in [1,2) from the two words:
+//   u1  = f1 - (1 - 2^-24)                     (exact)
+//   ang = fl32(f2*fl32(2*pi) - fl32(3*pi - pi*2^-23))   one FFMA;  ang ~= 2*pi*u2 - pi in (-pi, pi),
+//         where the MUFU sin/cos error bound (2^-21.4 abs) holds
+//   z0  = -sqrt(-2 ln u1) * cos(ang),  z1 = -sqrt(-2 ln u1) * sin(ang)       (cos(t+pi) = -cos t)
+// oracle/nes_oracle.py restates u1 and ang bit-exactly and evaluates ln/sqrt/sin/cos in fp64.
 __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float &z0, float &z1) {
-    const float u1 = u32_to_unit(xa);
-    const float u2 = u32_to_unit(xb);
-    // -2 ln u1 = (-2 ln 2) * lg2(u1)
-    const float nr = -sqrt_approx(-1.3862943611198906f * lg2_approx(u1));
-    const float ang = __fmaf_rn(u2, 6.283185307179586f, -3.141592653589793f);
+    const float u1 = u32_to_one_two(xa) - 0.99999994039535522f;
+    const float nr = -sqrt_approx(-1.3862943611198906f * lg2_approx(u1));     // -2 ln u = (-2 ln 2) lg2 u
+    const float ang = __fmaf_rn(u32_to_one_two(xb), kTwoPiF, -kAngOffF);
     z0 = nr * cos_approx(ang);
     z1 = nr * sin_approx(ang);
 }
 
 // The four normals of quad q of `member` at `gen`.
 __device__ __forceinline__ float4 noise_quad(uint32_t q, uint32_t member, uint32_t gen, uint32_t tag,
-                                             uint32_t k0, uint32_t k1) {
-    const uint4 x = philox4x32_10(q, member, gen, tag, k0, k1);
+                                             const PhiloxKey &key) {
+    const uint4 x = philox4x32_10(q, member, gen, tag, key);
     float4 z;
     box_muller(x.x, x.y, z.x, z.y);
     box_muller(x.z, x.w, z.z, z.w);

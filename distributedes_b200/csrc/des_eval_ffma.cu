@@ -25,7 +25,8 @@ struct EvalArgs {
     int T;
     int S;            // shared row stride in floats ((S/4) odd -> conflict-free float4 rows)
     float sigma, clip;
-    uint32_t k0, k1, gen;
+    PhiloxKey key;
+    uint32_t gen;
     uint64_t member_offset;
 };
 
@@ -34,11 +35,11 @@ __device__ __forceinline__ int round_up4(int x) { return (x + 3) & ~3; }
 // Generate theta'[off, off+cnt) into dst laid out as rows of K (row stride S); zero the K..Kp pad.
 __device__ __forceinline__ void gen_rows(float *__restrict__ dst, const float *__restrict__ theta, int off, int R,
                                          int K, int Kp, int S, float sigma, uint32_t member, uint32_t gen,
-                                         uint32_t k0, uint32_t k1) {
+                                         const PhiloxKey &key) {
     const int cnt = R * K;
     const int qa = off >> 2, qb = (off + cnt - 1) >> 2;
     for (int q = qa + (int)threadIdx.x; q <= qb; q += kThreads) {
-        const float4 z = noise_quad((uint32_t)q, member, gen, kStreamNesEps, k0, k1);
+        const float4 z = noise_quad((uint32_t)q, member, gen, kStreamNesEps, key);
         const float zz[4] = {z.x, z.y, z.z, z.w};
         int local = 4 * q - off;
         int r = (local >= 0) ? local / K : 0;
@@ -96,12 +97,12 @@ __global__ void __launch_bounds__(kThreads) eval_ffma_kernel(EvalArgs a) {
                 const int R = min(kRows, Nout - n0);
                 __syncthreads();            // previous chunk's readers of Ws/bias (and obs load) done
                 if (R > 0) {
-                    gen_rows(Ws, a.theta, off_w + n0 * K, R, K, Kp, S, a.sigma, member, gen, a.k0, a.k1);
+                    gen_rows(Ws, a.theta, off_w + n0 * K, R, K, Kp, S, a.sigma, member, gen, a.key);
                     // biases of the chunk: off_b + n0 .. + R
                     const int ob = off_b + n0;
                     const int qa = ob >> 2, qb = (ob + R - 1) >> 2;
                     for (int q = qa + (int)threadIdx.x; q <= qb; q += kThreads) {
-                        const float4 z = noise_quad((uint32_t)q, member, gen, kStreamNesEps, a.k0, a.k1);
+                        const float4 z = noise_quad((uint32_t)q, member, gen, kStreamNesEps, a.key);
                         const float zz[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -178,7 +179,7 @@ int eval_ffma_launch(float *fitness, const float *theta, const float *obs, const
     if (((S >> 2) & 1) == 0) S += 4;
     a.S = S;
     a.sigma = (float)sigma; a.clip = (float)clip;
-    a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32); a.gen = (uint32_t)generation;
+    a.key = make_philox_key(seed); a.gen = (uint32_t)generation;
     a.member_offset = (uint64_t)member_offset;
     const size_t smem = sizeof(float) * ((size_t)(2 * kTileT + kRows) * S + kRows);
     if (smem > 227 * 1024) {

@@ -20,8 +20,10 @@
 //   F16X3  every operand split x = hi + lo (fp16 each, ~22 bits); D += A_hi B_hi + A_lo B_hi + A_hi B_lo;
 //          accurate tanh.  ~fp32 accuracy at 3 MMAs per k-step.
 //
-// Warp roles: warp 0 = TMEM allocator + single-thread MMA issuer; warps 1..4*NT = epilogue (warp w owns
-// TMEM lane quadrant w%4 of tile slot (w-1)/4); the remaining 8 warps = weight generators.  All hand-offs
+// Warp roles (aligned to warpgroups so setmaxnreg can move registers from generators to epilogue warps):
+// warps [0, 4*NT) = epilogue (warp w owns TMEM lane quadrant w%4 of tile slot w/4); the next 16 warps =
+// weight generators; the last warp = TMEM allocator + single-thread MMA issuer.  X (the observation tape,
+// fp16, K padded to 64) sits in shared memory as the layer-1 A operand for the whole kernel.  All hand-offs
 // are mbarriers (generator -> MMA: slot_full/empty; MMA -> epilogue: acc_full/empty; epilogue -> MMA:
 // h_ready / h_free); accumulators are double buffered in TMEM in chunks of 64 columns.
 //
@@ -34,7 +36,7 @@ namespace des {
 
 using namespace tc;
 
-constexpr int kGenWarps = 8;
+constexpr int kGenWarps = 16;
 constexpr int kGenThreads = kGenWarps * 32;
 constexpr int kK1 = 32;        // layer-1 K (state_dim zero-padded): 2 k-steps of 16
 constexpr int kNC = 64;        // accumulator chunk: 64 output features = one MMA N
@@ -45,13 +47,12 @@ struct TcCfg {
     static constexpr bool X3 = (MODE == DES_FWD_F16X3);
     static constexpr int NCH = H / kNC;                       // output-feature chunks per layer
     static constexpr int KAT = H / 64;                        // 64-wide k atoms of layer 2
-    static constexpr int XCOLS = X3 ? kK1 : kK1 / 2;          // TMEM columns of X per tile (hi [+ lo])
     static constexpr int ACOLS = X3 ? H : H / 2;              // TMEM columns of H1 per tile slot
     static constexpr int SLOT_COLS = ACOLS + 2 * kNC;         // + two accumulator stages
     static constexpr int SLOT_BYTES = (X3 ? 2 : 1) * 64 * 128;   // one B tile: 64 rows x 128 B (hi [+ lo])
+    static constexpr int X_TILE_BYTES = (X3 ? 2 : 1) * 128 * 128;   // one X tile: 128 rows x 128 B (hi [+ lo])
     static constexpr int SMALL_FLOATS = 2 * H + kMaxA * H + kMaxA;   // b1, b2, W3'^T [H][8], b3[8]
-    // tile slots resident in TMEM at once (each needs SLOT_COLS); X for every tile of the tape is extra
-    static constexpr int NT_MAX = (512 - 4 * XCOLS) / SLOT_COLS >= 2 ? 2 : 1;
+    static constexpr int NT_MAX = 512 / SLOT_COLS >= 2 ? 2 : 1;     // tile slots resident in TMEM at once
 };
 
 struct TcArgs {
@@ -59,9 +60,10 @@ struct TcArgs {
     const float *theta, *obs, *target;
     const des_state *state;
     Layout L;
-    int T, n_tiles, nt, n_pass, n_slots;
+    int T, n_tiles, n_pass, n_slots;
     float sigma, clip;
-    uint32_t k0, k1, gen;
+    PhiloxKey key;
+    uint32_t gen;
     uint64_t member_offset;
     int64_t n_local;
 };
@@ -72,18 +74,17 @@ struct TcBars {
     uint64_t small_full[2], small_empty[2];
     uint64_t acc_full[2][2], acc_empty[2][2];
     uint64_t h_ready[2], h_free[2];
-    uint64_t x_ready;
     uint32_t tmem_base;
     float fit_part[16];
 };
 
 // eps for 8 consecutive flat parameters starting at j0 (multiple of 4): two quads.
 __device__ __forceinline__ void perturbed8(float (&w)[8], const float *__restrict__ theta, int j0, float sigma,
-                                           uint32_t member, uint32_t gen, uint32_t k0, uint32_t k1) {
+                                           uint32_t member, uint32_t gen, const PhiloxKey &key) {
     const float4 t0 = __ldg(reinterpret_cast<const float4 *>(theta + j0));
     const float4 t1 = __ldg(reinterpret_cast<const float4 *>(theta + j0 + 4));
-    const float4 z0 = noise_quad((uint32_t)(j0 >> 2), member, gen, kStreamNesEps, k0, k1);
-    const float4 z1 = noise_quad((uint32_t)(j0 >> 2) + 1, member, gen, kStreamNesEps, k0, k1);
+    const float4 z0 = noise_quad((uint32_t)(j0 >> 2), member, gen, kStreamNesEps, key);
+    const float4 z1 = noise_quad((uint32_t)(j0 >> 2) + 1, member, gen, kStreamNesEps, key);
     w[0] = __fmaf_rn(sigma, z0.x, t0.x); w[1] = __fmaf_rn(sigma, z0.y, t0.y);
     w[2] = __fmaf_rn(sigma, z0.z, t0.z); w[3] = __fmaf_rn(sigma, z0.w, t0.w);
     w[4] = __fmaf_rn(sigma, z1.x, t1.x); w[5] = __fmaf_rn(sigma, z1.y, t1.y);
@@ -92,8 +93,8 @@ __device__ __forceinline__ void perturbed8(float (&w)[8], const float *__restric
 
 // one perturbed parameter at arbitrary flat index j (slow path: whole quad per element)
 __device__ __forceinline__ float perturbed1(const float *__restrict__ theta, int j, float sigma, uint32_t member,
-                                            uint32_t gen, uint32_t k0, uint32_t k1) {
-    const float4 z = noise_quad((uint32_t)(j >> 2), member, gen, kStreamNesEps, k0, k1);
+                                            uint32_t gen, const PhiloxKey &key) {
+    const float4 z = noise_quad((uint32_t)(j >> 2), member, gen, kStreamNesEps, key);
     const int e = j & 3;
     const float zz = e == 0 ? z.x : (e == 1 ? z.y : (e == 2 ? z.z : z.w));
     return __fmaf_rn(sigma, zz, __ldg(theta + j));
@@ -113,23 +114,39 @@ __device__ __forceinline__ void store_octet(uint8_t *slot, int r, int c8, const 
     if (X3) *reinterpret_cast<uint4 *>(slot + 8192 + off) = lo;
 }
 
-template <int H, int MODE>
-__global__ void __launch_bounds__(544, 1) eval_tc_kernel(TcArgs a) {
+template <int REGS>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T (layer 1: A = X tile)
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <int H, int MODE, int NT>
+__global__ void __launch_bounds__((4 * NT + kGenWarps + 1) * 32, 1) eval_tc_kernel(TcArgs a) {
     using C = TcCfg<H, MODE>;
     constexpr bool X3 = C::X3;
+    constexpr int kEpiWarps = 4 * NT;
+    constexpr int kMmaWarp = kEpiWarps + kGenWarps;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *ring = smem;                                                        // n_slots * SLOT_BYTES
+    uint8_t *xs = smem;                                                          // n_tiles * X_TILE_BYTES
+    uint8_t *ring = xs + (size_t)a.n_tiles * C::X_TILE_BYTES;                    // n_slots * SLOT_BYTES
     float *small = reinterpret_cast<float *>(ring + (size_t)a.n_slots * C::SLOT_BYTES);   // [2][SMALL_FLOATS]
     TcBars *bars = reinterpret_cast<TcBars *>(small + 2 * C::SMALL_FLOATS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int NT = a.nt;
-    const int n_epi_warps = 4 * NT;
+    const int n_epi_warps = kEpiWarps;
     const Layout L = a.L;
     const uint32_t gen = a.state ? (uint32_t)a.state->generation : a.gen;
 
-    if (warp == 0) {
+    if (warp == kMmaWarp) {
         tmem_alloc(smem_u32(&bars->tmem_base), 512);
         if (lane == 0) {
             for (int s = 0; s < a.n_slots; ++s) {
@@ -146,30 +163,45 @@ __global__ void __launch_bounds__(544, 1) eval_tc_kernel(TcArgs a) {
                     mbar_init(smem_u32(&bars->acc_empty[p][st]), 4);
                 }
             }
-            mbar_init(smem_u32(&bars->x_ready), n_epi_warps);
             fence_barrier_init();
         }
     }
+    // X -> shared memory once: fp16 (hi [, lo]) K-major SWIZZLE_128B tiles of 128 observations, k < d0 (<= 32)
+    for (int idx = threadIdx.x; idx < a.n_tiles * 128 * 4; idx += blockDim.x) {
+        const int c8 = idx & 3, r = (idx >> 2) & 127, tt = idx >> 9;
+        const float *orow = a.obs + (int64_t)(tt * 128 + r) * L.d0;
+        float w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w[e] = (c8 * 8 + e < L.d0) ? __ldg(orow + c8 * 8 + e) : 0.f;
+        uint4 hi, lo;
+        if (X3) {
+            split_h2(w[0], w[1], hi.x, lo.x); split_h2(w[2], w[3], hi.y, lo.y);
+            split_h2(w[4], w[5], hi.z, lo.z); split_h2(w[6], w[7], hi.w, lo.w);
+        } else {
+            hi.x = pack_h2(w[0], w[1]); hi.y = pack_h2(w[2], w[3]); hi.z = pack_h2(w[4], w[5]); hi.w = pack_h2(w[6], w[7]);
+        }
+        const int off = r * 128 + ((c8 ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4 *>(xs + (size_t)tt * C::X_TILE_BYTES + off) = hi;
+        if (X3) *reinterpret_cast<uint4 *>(xs + (size_t)tt * C::X_TILE_BYTES + 16384 + off) = lo;
+    }
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
-    // TMEM map: X tiles at [0, n_tiles*XCOLS); tile slot ts at slot_base(ts): H1 [0,ACOLS), stages at ACOLS + st*64
-    const uint32_t x_cols_total = (uint32_t)(a.n_tiles * C::XCOLS);
-    auto slot_base = [&](int ts) { return tmem + x_cols_total + (uint32_t)(ts * C::SLOT_COLS); };
+    // TMEM map: tile slot ts at ts*SLOT_COLS: H1 [0,ACOLS), accumulator stages at ACOLS + st*64
+    auto slot_base = [&](int ts) { return tmem + (uint32_t)(ts * C::SLOT_COLS); };
 
     const int64_t first = blockIdx.x;
     const int64_t stride = gridDim.x;
 
-    if (warp == 0) {
+    if (warp == kMmaWarp) {
         // =================================== MMA issuer (one thread) ===================================
         if (lane == 0) {
             constexpr uint32_t idesc = idesc_f16(128, kNC);
             uint32_t slot_c = 0;                 // ring consume counter
             uint32_t acc_u[2] = {0, 0};          // accumulator-stage use counters per tile slot
             uint32_t hv[2] = {0, 0};             // (member, pass) counter per tile slot for h_ready
-            mbar_wait(smem_u32(&bars->x_ready), 0);
-            tc_fence_after();
             for (int64_t m = first; m < a.n_local; m += stride) {
                 for (int pass = 0; pass < a.n_pass; ++pass) {
                     // ---- layer 1: D1 chunk nc = X W1'[64nc:64nc+64, :]^T
@@ -184,15 +216,17 @@ __global__ void __launch_bounds__(544, 1) eval_tc_kernel(TcArgs a) {
                             mbar_wait(smem_u32(&bars->acc_empty[ts][st]), ph ^ 1);
                             tc_fence_after();
                             const uint32_t d = slot_base(ts) + C::ACOLS + st * kNC;
-                            const uint32_t xa = tmem + (uint32_t)((pass * NT + ts) * C::XCOLS);
+                            const uint32_t xaddr = smem_u32(xs + (size_t)(pass * NT + ts) * C::X_TILE_BYTES);
 #pragma unroll
                             for (int ks = 0; ks < kK1 / 16; ++ks) {
+                                const uint64_t ah = smem_desc_sw128(xaddr) + (uint64_t)(ks * 2);
                                 const uint64_t bh = smem_desc_sw128(bbase) + (uint64_t)(ks * 2);
-                                mma_f16_ts(d, xa + ks * 8, bh, idesc, ks > 0);
+                                mma_f16_ss(d, ah, bh, idesc, ks > 0);
                                 if (X3) {
+                                    const uint64_t al = smem_desc_sw128(xaddr + 16384) + (uint64_t)(ks * 2);
                                     const uint64_t bl = smem_desc_sw128(bbase + 8192) + (uint64_t)(ks * 2);
-                                    mma_f16_ts(d, xa + kK1 / 2 + ks * 8, bh, idesc, 1);    // X_lo * W_hi
-                                    mma_f16_ts(d, xa + ks * 8, bl, idesc, 1);              // X_hi * W_lo
+                                    mma_f16_ss(d, al, bh, idesc, 1);                      // X_lo * W_hi
+                                    mma_f16_ss(d, ah, bl, idesc, 1);                      // X_hi * W_lo
                                 }
                             }
                             mma_commit(smem_u32(&bars->acc_full[ts][st]));
@@ -242,30 +276,12 @@ __global__ void __launch_bounds__(544, 1) eval_tc_kernel(TcArgs a) {
                 }
             }
         }
-    } else if (warp <= n_epi_warps) {
+    } else if (warp < kEpiWarps) {
         // =================================== epilogue warps ============================================
-        const int ts = (warp - 1) >> 2;                               // tile slot
+        if (NT == 2) reg_alloc<96>();
+        const int ts = warp >> 2;                                     // tile slot
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
         const int row = (warp & 3) * 32 + lane;                       // observation row inside the tile
-        // --- X -> TMEM once, as fp16 (hi [, lo]) : tile tt is handled by the warps of slot tt % NT
-        for (int tt = ts; tt < a.n_tiles; tt += NT) {
-            const float *orow = a.obs + (int64_t)(tt * 128 + row) * L.d0;
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float x0 = (2 * i < L.d0) ? __ldg(orow + 2 * i) : 0.f;
-                const float x1 = (2 * i + 1 < L.d0) ? __ldg(orow + 2 * i + 1) : 0.f;
-                if (X3) split_h2(x0, x1, hi[i], lo[i]);
-                else hi[i] = pack_h2(x0, x1);
-            }
-            tmem_st16(tmem + lane_off + (uint32_t)(tt * C::XCOLS), hi);
-            if (X3) tmem_st16(tmem + lane_off + (uint32_t)(tt * C::XCOLS + 16), lo);
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars->x_ready));
-
         uint32_t acc_u = 0, hv = 0, mi = 0;
         const uint32_t sbase = slot_base(ts) + lane_off;
         for (int64_t m = first; m < a.n_local; m += stride, ++mi) {
@@ -379,11 +395,11 @@ __global__ void __launch_bounds__(544, 1) eval_tc_kernel(TcArgs a) {
             // ---- member done: reduce squared error over all rows / tile slots (fixed order -> deterministic)
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-            if (lane == 0) bars->fit_part[warp - 1] = sq;
+            if (lane == 0) bars->fit_part[warp] = sq;
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars->small_empty[p]));     // done with this member's b/W3
             asm volatile("bar.sync 1, %0;" ::"r"(n_epi_warps * 32) : "memory");
-            if (warp == 1 && lane == 0) {
+            if (warp == 0 && lane == 0) {
                 double f = 0.0;
                 for (int w = 0; w < n_epi_warps; ++w) f += (double)bars->fit_part[w];
                 a.fitness[m] = (float)(-f);
@@ -392,8 +408,14 @@ __global__ void __launch_bounds__(544, 1) eval_tc_kernel(TcArgs a) {
         }
     } else {
         // =================================== weight generators =========================================
-        const int gtid = threadIdx.x - (1 + n_epi_warps) * 32;          // 0..255
+        if (NT == 2) reg_dealloc<56>();
+        const int gtid = threadIdx.x - kEpiWarps * 32;                  // 0..511
         uint32_t slot_p = 0, mi = 0;
+        // theta of this thread's W2 octet is prefetched one ring slot ahead (it does not depend on the member)
+        const int r2 = gtid >> 3, c82 = gtid & 7;
+        auto w2_index = [&](int nc, int ka) { return L.off_w2 + (nc * 64 + r2) * H + ka * 64 + c82 * 8; };
+        float4 tn0 = __ldg(reinterpret_cast<const float4 *>(a.theta + w2_index(0, 0)));
+        float4 tn1 = __ldg(reinterpret_cast<const float4 *>(a.theta + w2_index(0, 0) + 4));
         for (int64_t m = first; m < a.n_local; m += stride, ++mi) {
             const uint32_t member = (uint32_t)(a.member_offset + (uint64_t)m);
             // ---- small fp32 arrays: b1 | b2 | W3[8][H] | b3[8]
@@ -401,17 +423,17 @@ __global__ void __launch_bounds__(544, 1) eval_tc_kernel(TcArgs a) {
             float *sm = small + p * C::SMALL_FLOATS;
             mbar_wait(smem_u32(&bars->small_empty[p]), ((mi >> 1) & 1) ^ 1);
             for (int i = gtid; i < H / 4; i += kGenThreads) {                // b1, b2: aligned quads
-                const float4 z1 = noise_quad((uint32_t)((L.off_b1 >> 2) + i), member, gen, kStreamNesEps, a.k0, a.k1);
+                const float4 z1 = noise_quad((uint32_t)((L.off_b1 >> 2) + i), member, gen, kStreamNesEps, a.key);
                 const float4 t1 = __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_b1) + i);
                 reinterpret_cast<float4 *>(sm)[i] = make_float4(__fmaf_rn(a.sigma, z1.x, t1.x), __fmaf_rn(a.sigma, z1.y, t1.y),
                                                                 __fmaf_rn(a.sigma, z1.z, t1.z), __fmaf_rn(a.sigma, z1.w, t1.w));
-                const float4 z2 = noise_quad((uint32_t)((L.off_b2 >> 2) + i), member, gen, kStreamNesEps, a.k0, a.k1);
+                const float4 z2 = noise_quad((uint32_t)((L.off_b2 >> 2) + i), member, gen, kStreamNesEps, a.key);
                 const float4 t2 = __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_b2) + i);
                 reinterpret_cast<float4 *>(sm + H)[i] = make_float4(__fmaf_rn(a.sigma, z2.x, t2.x), __fmaf_rn(a.sigma, z2.y, t2.y),
                                                                     __fmaf_rn(a.sigma, z2.z, t2.z), __fmaf_rn(a.sigma, z2.w, t2.w));
             }
             for (int i = gtid; i < L.A * H / 4; i += kGenThreads) {          // W3' rows are H floats: aligned quads
-                const float4 z = noise_quad((uint32_t)((L.off_w3 >> 2) + i), member, gen, kStreamNesEps, a.k0, a.k1);
+                const float4 z = noise_quad((uint32_t)((L.off_w3 >> 2) + i), member, gen, kStreamNesEps, a.key);
                 const float4 t = __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_w3) + i);
                 const int q = (4 * i) / H, n = (4 * i) - q * H;               // stored transposed: w3t[n][q]
                 float *dst = sm + 2 * H + n * kMaxA + q;
@@ -423,7 +445,7 @@ __global__ void __launch_bounds__(544, 1) eval_tc_kernel(TcArgs a) {
             if (mi < 2)                                                       // unused action columns stay zero (finite)
                 for (int i = gtid; i < H * kMaxA; i += kGenThreads)
                     if ((i & (kMaxA - 1)) >= L.A) sm[2 * H + i] = 0.f;
-            if (gtid < L.A) sm[2 * H + kMaxA * H + gtid] = perturbed1(a.theta, L.off_b3 + gtid, a.sigma, member, gen, a.k0, a.k1);
+            if (gtid < L.A) sm[2 * H + kMaxA * H + gtid] = perturbed1(a.theta, L.off_b3 + gtid, a.sigma, member, gen, a.key);
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars->small_full[p]));
 
@@ -434,7 +456,7 @@ __global__ void __launch_bounds__(544, 1) eval_tc_kernel(TcArgs a) {
                     ++slot_p;
                     mbar_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
                     uint8_t *slot = ring + (size_t)s * C::SLOT_BYTES;
-                    {   // 64 rows x 4 octets = 256 items: one per thread
+                    if (gtid < 256) {   // 64 rows x 4 octets = 256 items
                         const int r = gtid >> 2, c8 = gtid & 3;
                         const int n = nc * 64 + r;
                         float w[8];
@@ -445,7 +467,7 @@ __global__ void __launch_bounds__(544, 1) eval_tc_kernel(TcArgs a) {
                                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                                 if (k < L.d0) {
                                     const int j = L.off_w1 + n * L.d0 + k;
-                                    const float4 z = noise_quad((uint32_t)(j >> 2), member, gen, kStreamNesEps, a.k0, a.k1);
+                                    const float4 z = noise_quad((uint32_t)(j >> 2), member, gen, kStreamNesEps, a.key);
                                     const float4 t = __ldg(reinterpret_cast<const float4 *>(a.theta + j));
                                     v = make_float4(__fmaf_rn(a.sigma, z.x, t.x), __fmaf_rn(a.sigma, z.y, t.y),
                                                     __fmaf_rn(a.sigma, z.z, t.z), __fmaf_rn(a.sigma, z.w, t.w));
@@ -456,7 +478,7 @@ __global__ void __launch_bounds__(544, 1) eval_tc_kernel(TcArgs a) {
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
                                 const int k = c8 * 8 + e;
-                                w[e] = (k < L.d0) ? perturbed1(a.theta, L.off_w1 + n * L.d0 + k, a.sigma, member, gen, a.k0, a.k1) : 0.f;
+                                w[e] = (k < L.d0) ? perturbed1(a.theta, L.off_w1 + n * L.d0 + k, a.sigma, member, gen, a.key) : 0.f;
                             }
                         }
                         store_octet<X3>(slot, r, c8, w);
@@ -470,16 +492,23 @@ __global__ void __launch_bounds__(544, 1) eval_tc_kernel(TcArgs a) {
                     for (int ka = 0; ka < C::KAT; ++ka) {
                         const uint32_t s = slot_p % a.n_slots, sph = (slot_p / a.n_slots) & 1;
                         ++slot_p;
-                        mbar_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
                         uint8_t *slot = ring + (size_t)s * C::SLOT_BYTES;
-#pragma unroll
-                        for (int it = 0; it < 2; ++it) {                      // 512 octets / 256 threads
-                            const int oct = gtid + it * kGenThreads;
-                            const int r = oct >> 3, c8 = oct & 7;
+                        {   // 64 rows x 8 octets = 512 items: one per thread
+                            const float4 t0 = tn0, t1 = tn1;
+                            int nnc = nc, nka = ka + 1;                       // next slot (wraps to the next member)
+                            if (nka == C::KAT) { nka = 0; if (++nnc == C::NCH) nnc = 0; }
+                            tn0 = __ldg(reinterpret_cast<const float4 *>(a.theta + w2_index(nnc, nka)));
+                            tn1 = __ldg(reinterpret_cast<const float4 *>(a.theta + w2_index(nnc, nka) + 4));
+                            const int j0 = w2_index(nc, ka);
+                            const float4 z0 = noise_quad((uint32_t)(j0 >> 2), member, gen, kStreamNesEps, a.key);
+                            const float4 z1 = noise_quad((uint32_t)(j0 >> 2) + 1, member, gen, kStreamNesEps, a.key);
                             float w[8];
-                            perturbed8(w, a.theta, L.off_w2 + (nc * 64 + r) * H + ka * 64 + c8 * 8, a.sigma, member, gen,
-                                       a.k0, a.k1);
-                            store_octet<X3>(slot, r, c8, w);
+                            w[0] = __fmaf_rn(a.sigma, z0.x, t0.x); w[1] = __fmaf_rn(a.sigma, z0.y, t0.y);
+                            w[2] = __fmaf_rn(a.sigma, z0.z, t0.z); w[3] = __fmaf_rn(a.sigma, z0.w, t0.w);
+                            w[4] = __fmaf_rn(a.sigma, z1.x, t1.x); w[5] = __fmaf_rn(a.sigma, z1.y, t1.y);
+                            w[6] = __fmaf_rn(a.sigma, z1.z, t1.z); w[7] = __fmaf_rn(a.sigma, z1.w, t1.w);
+                            mbar_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
+                            store_octet<X3>(slot, r2, c82, w);
                         }
                         fence_proxy_async_smem();
                         __syncwarp();
@@ -491,36 +520,42 @@ __global__ void __launch_bounds__(544, 1) eval_tc_kernel(TcArgs a) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
+    if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
+}
+
+template <int H, int MODE, int NT>
+static int launch_tc_nt(TcArgs &a, cudaStream_t st) {
+    using C = TcCfg<H, MODE>;
+    a.n_pass = a.n_tiles / NT;
+    const size_t fixed = 2 * C::SMALL_FLOATS * sizeof(float) + sizeof(TcBars) + 1024;
+    const size_t xbytes = (size_t)a.n_tiles * C::X_TILE_BYTES;
+    const int per_member = C::NCH + C::NCH * C::KAT;
+    int n_slots = xbytes + fixed >= 227 * 1024 ? 0 : (int)((227 * 1024 - fixed - xbytes) / C::SLOT_BYTES);
+    if (n_slots > 32) n_slots = 32;
+    if (n_slots > 2 * per_member) n_slots = 2 * per_member;
+    if (n_slots < 4) {
+        set_error("des_nes_eval(tensor): tape_len %d leaves no shared memory for the weight ring (H=%d)", a.T, H);
+        return DES_ERR_UNSUPPORTED;
+    }
+    a.n_slots = n_slots;
+    const size_t smem = xbytes + (size_t)n_slots * C::SLOT_BYTES + fixed;
+    int dev = 0, sms = 148;
+    DES_CUDA(cudaGetDevice(&dev));
+    DES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    DES_CUDA(cudaFuncSetAttribute(eval_tc_kernel<H, MODE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = a.n_local < sms ? a.n_local : sms;
+    const int threads = (4 * NT + kGenWarps + 1) * 32;
+    eval_tc_kernel<H, MODE, NT><<<(unsigned)grid, threads, smem, st>>>(a);
+    DES_LAUNCH_CHECK("eval_tc_kernel");
+    return DES_OK;
 }
 
 template <int H, int MODE>
 static int launch_tc(TcArgs &a, cudaStream_t st) {
     using C = TcCfg<H, MODE>;
     a.n_tiles = a.T / 128;
-    a.nt = (C::NT_MAX >= 2 && a.n_tiles % 2 == 0) ? 2 : 1;
-    a.n_pass = a.n_tiles / a.nt;
-    if (a.n_tiles * C::XCOLS + a.nt * C::SLOT_COLS > 512) {
-        set_error("des_nes_eval(tensor): tape_len %d needs %d TMEM columns (> 512) for H=%d", a.T,
-                  a.n_tiles * C::XCOLS + a.nt * C::SLOT_COLS, H);
-        return DES_ERR_UNSUPPORTED;
-    }
-    const size_t fixed = 2 * C::SMALL_FLOATS * sizeof(float) + sizeof(TcBars) + 1024;
-    int n_slots = (int)((227 * 1024 - fixed) / C::SLOT_BYTES);
-    if (n_slots > 32) n_slots = 32;
-    const int per_member = C::NCH + C::NCH * C::KAT;
-    if (n_slots > 2 * per_member) n_slots = 2 * per_member;
-    a.n_slots = n_slots;
-    const size_t smem = (size_t)n_slots * C::SLOT_BYTES + fixed;
-    int dev = 0, sms = 148;
-    DES_CUDA(cudaGetDevice(&dev));
-    DES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    DES_CUDA(cudaFuncSetAttribute(eval_tc_kernel<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t grid = a.n_local < sms ? a.n_local : sms;
-    const int threads = (1 + 4 * a.nt + kGenWarps) * 32;
-    eval_tc_kernel<H, MODE><<<(unsigned)grid, threads, smem, st>>>(a);
-    DES_LAUNCH_CHECK("eval_tc_kernel");
-    return DES_OK;
+    if (C::NT_MAX >= 2 && a.n_tiles % 2 == 0) return launch_tc_nt<H, MODE, (C::NT_MAX >= 2 ? 2 : 1)>(a, st);
+    return launch_tc_nt<H, MODE, 1>(a, st);
 }
 
 int eval_tc_launch(float *fitness, const float *theta, const float *obs, const float *target, des_dims dims,
@@ -542,7 +577,7 @@ int eval_tc_launch(float *fitness, const float *theta, const float *obs, const f
     a.L = Layout(dims.state_dim, H, dims.action_dim);
     a.T = dims.tape_len;
     a.sigma = (float)sigma; a.clip = (float)clip;
-    a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32); a.gen = (uint32_t)generation;
+    a.key = make_philox_key(seed); a.gen = (uint32_t)generation;
     a.member_offset = (uint64_t)member_offset; a.n_local = n_local;
     const bool x3 = precision == DES_FWD_F16X3;
     switch (H) {

@@ -8,7 +8,7 @@ namespace des {
 // One thread per (member, quad).  Rows are P floats with arbitrary P, so stores are scalar and guarded.
 template <bool kPerturb>
 __global__ void noise_rows_kernel(float *__restrict__ out, const float *__restrict__ theta, int64_t n_members,
-                                  int64_t P, float sigma, uint32_t k0, uint32_t k1, uint32_t gen,
+                                  int64_t P, float sigma, PhiloxKey key, uint32_t gen,
                                   uint32_t tag, uint64_t member_offset) {
     const int64_t nq = (P + 3) >> 2;
     const int64_t total = n_members * nq;
@@ -16,7 +16,7 @@ __global__ void noise_rows_kernel(float *__restrict__ out, const float *__restri
          idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t m = idx / nq;
         const int64_t q = idx - m * nq;
-        const float4 z = noise_quad((uint32_t)q, (uint32_t)(member_offset + m), gen, tag, k0, k1);
+        const float4 z = noise_quad((uint32_t)q, (uint32_t)(member_offset + m), gen, tag, key);
         const float zz[4] = {z.x, z.y, z.z, z.w};
         float *row = out + m * P;
 #pragma unroll
@@ -34,12 +34,12 @@ static int launch_rows(bool perturb, float *out, const float *theta, int64_t n, 
     const int threads = 256;
     int64_t blocks = (total + threads - 1) / threads;
     if (blocks > 148 * 64) blocks = 148 * 64;
-    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const PhiloxKey key = make_philox_key(seed);
     if (perturb)
-        noise_rows_kernel<true><<<(unsigned)blocks, threads, 0, st>>>(out, theta, n, P, (float)sigma, k0, k1,
+        noise_rows_kernel<true><<<(unsigned)blocks, threads, 0, st>>>(out, theta, n, P, (float)sigma, key,
                                                                       (uint32_t)gen, tag, (uint64_t)member_offset);
     else
-        noise_rows_kernel<false><<<(unsigned)blocks, threads, 0, st>>>(out, nullptr, n, P, 0.f, k0, k1,
+        noise_rows_kernel<false><<<(unsigned)blocks, threads, 0, st>>>(out, nullptr, n, P, 0.f, key,
                                                                        (uint32_t)gen, tag, (uint64_t)member_offset);
     DES_LAUNCH_CHECK("noise_rows_kernel");
     return DES_OK;

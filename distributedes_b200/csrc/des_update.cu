@@ -45,7 +45,7 @@ __host__ inline GradPlan grad_plan(int64_t n_local, int64_t P) {
 
 __global__ void __launch_bounds__(kGradThreads) grad_chunk_kernel(float *__restrict__ ws, const float *__restrict__ shaped,
                                                                    int64_t n_local, int64_t nq, int64_t Ppad,
-                                                                   int64_t per_chunk, uint32_t k0, uint32_t k1,
+                                                                   int64_t per_chunk, PhiloxKey key,
                                                                    uint32_t gen_arg, const des_state *state,
                                                                    uint64_t member_offset) {
     const int64_t q = (int64_t)blockIdx.x * kGradThreads + threadIdx.x;
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kGradThreads) grad_chunk_kernel(float *__restr
 #pragma unroll 2
     for (int64_t i = i0; i < i1; ++i) {
         const float s = __ldg(shaped + i);     // warp-uniform broadcast load
-        const float4 z = noise_quad((uint32_t)q, (uint32_t)(member_offset + i), gen, kStreamNesEps, k0, k1);
+        const float4 z = noise_quad((uint32_t)q, (uint32_t)(member_offset + i), gen, kStreamNesEps, key);
         acc.x = __fmaf_rn(s, z.x, acc.x);
         acc.y = __fmaf_rn(s, z.y, acc.y);
         acc.z = __fmaf_rn(s, z.z, acc.z);
@@ -149,7 +149,7 @@ extern "C" DES_API int des_nes_grad_partial(float *partial_out_dev, const float 
     float *ws = (float *)workspace_dev;
     const unsigned bx = (unsigned)((p.nq + kGradThreads - 1) / kGradThreads);
     grad_chunk_kernel<<<dim3(bx, (unsigned)p.chunks), kGradThreads, 0, st>>>(
-        ws, shaped_local_dev, n_local, p.nq, p.Ppad, p.per_chunk, (uint32_t)seed, (uint32_t)(seed >> 32),
+        ws, shaped_local_dev, n_local, p.nq, p.Ppad, p.per_chunk, make_philox_key(seed),
         (uint32_t)generation, state_dev, (uint64_t)member_offset);
     DES_LAUNCH_CHECK("grad_chunk_kernel");
     grad_reduce_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(partial_out_dev, ws, P, p.Ppad, p.chunks);

@@ -20,8 +20,10 @@
  *        | fc3.weight (A x H) | fc3.bias (A)]
  *   - Noise contract: eps[member][j] is a pure function of (seed, generation, GLOBAL member index,
  *     j): Philox4x32-10, counter = (j/4, member, generation, stream_tag), key = (seed_lo, seed_hi);
- *     words (x0,x1) -> Box-Muller -> (eps[4q], eps[4q+1]); (x2,x3) -> (eps[4q+2], eps[4q+3]);
- *     u = fma(float(x), 2^-32, 2^-33); z_cos = sqrt(-2 ln u1) cos(2 pi u2), z_sin likewise.
+ *     words (x0,x1) -> Box-Muller -> (eps[4q], eps[4q+1]); (x2,x3) -> (eps[4q+2], eps[4q+3]).
+ *     Box-Muller on the LOW 23 bits k of each word, f = 1 + k*2^-23:  u1 = f1 - (1 - 2^-24) in (0,1),
+ *     ang = fl32(f2*fl32(2 pi) - fl32(3 pi - pi 2^-23)) ~ 2 pi u2 - pi,
+ *     z_first = -sqrt(-2 ln u1) cos(ang), z_second = -sqrt(-2 ln u1) sin(ang).
  *     (oracle/nes_oracle.py restates it bit-exactly for the uint32 words.)  It replaces
  *     np.random.randn at natural_es.py:29; eps never crosses a process/GPU boundary.
  */

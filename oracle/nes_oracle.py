@@ -60,23 +60,26 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return (c0.astype(np.uint32), c1.astype(np.uint32), c2.astype(np.uint32), c3.astype(np.uint32))
 
 
-def u32_to_unit_f32(x):
-    """uint32 -> fp32 uniform in (0, 1]:  fma(float(x), 2^-32, 2^-33), all roundings fp32 RN.
+_TWO_PI_F = float(np.float32(6.283185307179586))              # fl32(2*pi)
+_ANG_OFF_F = float(np.float32(9.424777586262351))             # fl32(3*pi - pi*2^-23)
+_ONE_M = float(np.float32(1.0 - 2.0 ** -24))                  # fl32(1 - 2^-24)
 
-    The CUDA side does ``__fmaf_rn(__uint2float_rn(x), 0x1p-32f, 0x1p-33f)``.  float(x)*2^-32 is
-    exact (power-of-two scale), so the fma is one rounding of (float(x)*2^-32 + 2^-33): computing it
-    in fp64 (exact) and rounding once to fp32 reproduces the fused result bit for bit.
-    """
-    xf = np.asarray(x, dtype=np.uint32).astype(np.float32)          # RN conversion
-    return (xf.astype(np.float64) * 2.0 ** -32 + 2.0 ** -33).astype(np.float32)
+
+def u32_to_one_two(x):
+    """f = 1 + k*2^-23 in [1,2) from the LOW 23 bits k of the word (exact; the CUDA side is one LOP3:
+    as_float(0x3F800000 | (x & 0x7FFFFF))).  Returned as float64."""
+    k = (np.asarray(x, dtype=np.uint32) & np.uint32(0x7FFFFF)).astype(np.float64)
+    return 1.0 + k * 2.0 ** -23
 
 
 def box_muller(xa, xb):
-    """(z_cos, z_sin) = sqrt(-2 ln u1) * (cos 2*pi*u2, sin 2*pi*u2); fp64 on the fp32 uniforms."""
-    u1 = u32_to_unit_f32(xa).astype(np.float64)
-    u2 = u32_to_unit_f32(xb).astype(np.float64)
-    r = np.sqrt(-2.0 * np.log(u1))
-    ang = 2.0 * np.pi * u2
+    """The noise contract of include/des_b200.h, fp32 intermediates restated bit-exactly:
+         u1  = f1 - (1 - 2^-24)                      = (2k1+1)*2^-24 in (0,1), exact in fp32
+         ang = fl32(f2*fl32(2 pi) - fl32(3 pi - pi 2^-23))   one fused rounding; ~ 2 pi u2 - pi in (-pi, pi)
+         z0  = -sqrt(-2 ln u1) cos(ang),  z1 = -sqrt(-2 ln u1) sin(ang)      (ln/sqrt/sin/cos in fp64 here)"""
+    u1 = u32_to_one_two(xa) - _ONE_M
+    ang = (u32_to_one_two(xb) * _TWO_PI_F - _ANG_OFF_F).astype(np.float32).astype(np.float64)
+    r = -np.sqrt(-2.0 * np.log(u1))
     return r * np.cos(ang), r * np.sin(ang)
 
 

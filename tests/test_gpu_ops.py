@@ -57,8 +57,11 @@ def test_perturb_matches_oracle():
     P = orc.param_count(d0, H, A)
     theta = orc.synthetic_theta(d0, H, A)
     got = ops().nes_perturb(torch.from_numpy(theta).to(DEV), 6, 0.1, 42, 5, member_offset=10).cpu().numpy()
-    ref = orc.perturb(theta[None], 0.1, orc.noise(42, 5, 10, 6, P))
-    assert np.max(np.abs(got.astype(np.float64) - ref)) <= 0.1 * 4e-6 * 8 + 1e-7
+    eps = orc.noise(42, 5, 10, 6, P)
+    ref = orc.perturb(theta[None], 0.1, eps)
+    r = np.sqrt((eps ** 2).reshape(6, -1, 2).sum(-1)).repeat(2, axis=1)
+    tol = 0.1 * (noise_tol(eps) + 2.0 ** -22 * np.log(2) / np.maximum(r, 1e-4)) + 1e-7     # sigma * noise bound + 1 ulp
+    assert np.all(np.abs(got.astype(np.float64) - ref) <= tol)
 
 
 CASES = [  # d0, H, A, T, clip, n_local, offset

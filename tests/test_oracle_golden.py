@@ -37,10 +37,13 @@ def test_noise_is_standard_normal_and_counter_based():
 
 
 def test_unit_uniform_edges():
-    u = orc.u32_to_unit_f32(np.asarray([0, 1, 2 ** 31, 2 ** 32 - 1], dtype=np.uint32))
-    assert u.dtype == np.float32
-    assert u[0] == np.float32(2.0 ** -33) and u[-1] == np.float32(1.0)
-    assert np.all(u > 0) and np.all(u <= 1)
+    f = orc.u32_to_one_two(np.asarray([0, 1, 0x7FFFFF, 0x800000, 0xFFFFFFFF], dtype=np.uint32))
+    assert f[0] == 1.0 and f[1] == 1.0 + 2.0 ** -23 and f[2] == 2.0 - 2.0 ** -23
+    assert f[3] == 1.0 and f[4] == f[2]                       # only the low 23 bits count
+    z0, z1 = orc.box_muller(np.asarray([0, 0x7FFFFF], dtype=np.uint32), np.asarray([0, 0x400000], dtype=np.uint32))
+    assert np.all(np.isfinite(z0)) and np.all(np.isfinite(z1))
+    assert abs(np.hypot(z0[0], z1[0]) - np.sqrt(2 * 24 * np.log(2))) < 1e-12      # u1 = 2^-24: the 5.77 sigma tail
+    assert np.hypot(z0[1], z1[1]) < 4e-4                                          # u1 = 1 - 2^-24
 
 
 def test_fitness_shift_matches_reference(golden_dir):
