@@ -43,7 +43,9 @@ def parse():
     ap.add_argument('--state-dim', type=int, default=24)
     ap.add_argument('--action-dim', type=int, default=4)
     ap.add_argument('--tape-len', type=int, default=256)
-    ap.add_argument('--precision', default=os.environ.get('DES_BENCH_PRECISION', 'fp32'))
+    ap.add_argument('--precision', default=os.environ.get('DES_BENCH_PRECISION', 'f16x3'),
+                    help='policy-forward arithmetic: f16x3 (tensor cores, fp32-grade, default), f16 (tensor cores, fp16 operands), fp32 (CUDA cores)')
+    ap.add_argument('--no-other-modes', action='store_true', help='skip the short extra measurement of the other tensor-core mode')
     ap.add_argument('--cpu-sample', type=int, default=0, help='members per CPU-baseline step (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
@@ -212,7 +214,7 @@ def run_ours(a):
     def eval_only():
         eng.k.nes_eval(eng.theta, eng.obs, eng.target, hidden=H, sigma=eng.sigma, clip=eng.clip, seed=eng.seed,
                        state=eng.state, member_offset=eng.offset, n_local=eng.n_local, precision=eng.precision,
-                       out=eng.fitness_all[eng.offset:eng.offset + eng.n_local])
+                       out=eng.fitness_all[eng.offset:eng.offset + eng.n_local], workspace=eng.eval_ws)
     for _ in range(2):
         eval_only()
     ev_ms, _ = timed(eval_only, a.steps)
@@ -258,6 +260,25 @@ def run_ours(a):
            'd2h_bytes_per_step': int(theta_h.numel() * 4 + fit_h.numel() * 4),
            'api': 'NESEngine.generation_host (pinned host tape in, theta + fitness out, synchronous)'}
 
+    # ---- the other tensor-core mode, device-resident, for context (not the headline) ----
+    other = None
+    if not a.no_other_modes and a.precision in ('f16', 'f16x3'):
+        oprec = 'f16' if a.precision == 'f16x3' else 'f16x3'
+        try:
+            eng2 = NESEngine(state_dim=d0, hidden=H, action_dim=A, pop_size=N, theta0=theta0, obs=obs, target=target,
+                             sigma=0.1, learning_rate=0.1, weight_decay=0.005, clip=1.0, seed=0, precision=oprec,
+                             device=dev, use_graph=not a.no_graph)
+            for _ in range(3):
+                eng2.generation()
+            o_ms, _ = timed(eng2.generation, max(3, a.steps // 2))
+            o_ms = max_over_ranks(o_ms) / max(3, a.steps // 2)
+            other = {oprec: {'ms_per_step': o_ms, 'value': N / (o_ms * 1e-3), 'unit': 'policy-evals/s',
+                             'note': 'fp16-rounded operands (11 significant bits, like TF32): fitness within 4e-3 of the oracle'
+                             if oprec == 'f16' else 'hi/lo split operands: fitness within 3e-5 of the oracle'}}
+            del eng2
+        except Exception as e:
+            other = {oprec: {'error': str(e)[:200]}}
+
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -273,7 +294,8 @@ def run_ours(a):
         line = {
             'metric': 'nes_policy_evals_per_sec', 'value': value, 'unit': 'policy-evals/s', 'n_gpus': world,
             'steps': a.steps, 'warmup': max(a.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
-            'scaling': 'strong', 'vs_baseline': None, 'dtype': {'fp32': 'f32', 'f16': 'f16', 'f16x3': 'f16x3'}[a.precision],
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': {'fp32': 'f32', 'f16': 'f16 (fp16 operands, f32 accumulate)',
+                                                           'f16x3': 'f16x3 (split-fp16 operands ~ f32, f32 accumulate)'}[a.precision],
             'data': 'synthetic', 'generations_per_sec': 1e3 / ms_per_step,
             'forwards_per_sec': value * T,
             'config': {'workload': workload_name(a), 'precision': a.precision, 'param_count': P,
@@ -281,7 +303,7 @@ def run_ours(a):
                        'l2': 'flushed: 256 MiB memset between steps, outside the per-step CUDA events',
                        'parallelism': 'population sharded over %d GPU(s); all-reduce fitness[N] + all-reduce partial[P]' % world},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches_per_step * a.steps,
-            'roofline': roofline, 'cpu_baseline': cpu,
+            'roofline': roofline, 'cpu_baseline': cpu, 'other_modes': other,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

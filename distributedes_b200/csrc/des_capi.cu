@@ -26,7 +26,9 @@ int eval_ffma_launch(float *fitness, const float *theta, const float *obs, const
                      int64_t member_offset, int64_t n_local, cudaStream_t st);
 int eval_tc_launch(float *fitness, const float *theta, const float *obs, const float *target, des_dims dims,
                    double sigma, double clip, uint64_t seed, uint64_t generation, const des_state *state,
-                   int64_t member_offset, int64_t n_local, int precision, cudaStream_t st);
+                   int64_t member_offset, int64_t n_local, int precision, void *workspace, size_t workspace_bytes,
+                   cudaStream_t st);
+size_t eval_tc_workspace_bytes(des_dims dims, int precision);
 
 }  // namespace des
 
@@ -42,6 +44,11 @@ extern "C" DES_API int des_device_count(void) {
     return n;
 }
 
+extern "C" DES_API size_t des_nes_eval_workspace_bytes(des_dims dims, int precision) {
+    if (precision == DES_FWD_F16 || precision == DES_FWD_F16X3) return des::eval_tc_workspace_bytes(dims, precision);
+    return 0;
+}
+
 extern "C" DES_API int64_t des_param_count(int32_t d0, int32_t H, int32_t A) {
     if (d0 <= 0 || H <= 0 || A <= 0) return -1;
     return (int64_t)d0 * H + H + (int64_t)H * H + H + (int64_t)H * A + A;
@@ -50,7 +57,7 @@ extern "C" DES_API int64_t des_param_count(int32_t d0, int32_t H, int32_t A) {
 extern "C" DES_API int des_nes_eval(float *fitness_out_dev, const float *theta_dev, const float *obs_dev, const float *target_dev,
                             des_dims dims, double sigma, double clip, uint64_t seed, uint64_t generation,
                             const des_state *state_dev, int64_t member_offset, int64_t n_local, int precision,
-                            void *stream) {
+                            void *workspace_dev, size_t workspace_bytes, void *stream) {
     using namespace des;
     DES_REQUIRE(dims.state_dim > 0 && dims.hidden > 0 && dims.action_dim > 0 && dims.tape_len > 0,
                 "des_nes_eval: bad dims (d0=%d H=%d A=%d T=%d)", dims.state_dim, dims.hidden, dims.action_dim,
@@ -71,7 +78,7 @@ extern "C" DES_API int des_nes_eval(float *fitness_out_dev, const float *theta_d
         case DES_FWD_F16:
         case DES_FWD_F16X3:
             return eval_tc_launch(fitness_out_dev, theta_dev, obs_dev, target_dev, dims, sigma, clip, seed, generation,
-                                  state_dev, member_offset, n_local, precision, st);
+                                  state_dev, member_offset, n_local, precision, workspace_dev, workspace_bytes, st);
         default:
             set_error("des_nes_eval: unknown precision %d", precision);
             return DES_ERR_INVALID_ARGUMENT;
@@ -91,15 +98,15 @@ struct des_session {
     float *theta, *obs, *target, *fitness_all, *shaped, *partial, *update;
     double *adam_m, *adam_v;
     des_state *state;
-    void *rank_ws, *grad_ws;
-    size_t rank_ws_bytes, grad_ws_bytes;
+    void *rank_ws, *grad_ws, *eval_ws;
+    size_t rank_ws_bytes, grad_ws_bytes, eval_ws_bytes;
 };
 
 static void session_free(des_session *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     void *ptrs[] = {s->theta, s->obs, s->target, s->fitness_all, s->shaped, s->partial, s->update,
-                    s->adam_m, s->adam_v, s->state, s->rank_ws, s->grad_ws};
+                    s->adam_m, s->adam_v, s->state, s->rank_ws, s->grad_ws, s->eval_ws};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -157,6 +164,8 @@ extern "C" DES_API int des_session_create(des_session **out, int device, des_dim
     s->grad_ws_bytes = des_grad_workspace_bytes(n_local, P) + 16;
     DES_S_CUDA(cudaMalloc(&s->rank_ws, s->rank_ws_bytes));
     DES_S_CUDA(cudaMalloc(&s->grad_ws, s->grad_ws_bytes));
+    s->eval_ws_bytes = des_nes_eval_workspace_bytes(dims, precision);
+    if (s->eval_ws_bytes) DES_S_CUDA(cudaMalloc(&s->eval_ws, s->eval_ws_bytes));
     DES_S_CUDA(cudaMemsetAsync(s->adam_m, 0, P * sizeof(double), s->stream));
     DES_S_CUDA(cudaMemsetAsync(s->adam_v, 0, P * sizeof(double), s->stream));
     DES_S_CUDA(cudaMemsetAsync(s->fitness_all, 0, N * sizeof(float), s->stream));
@@ -187,7 +196,8 @@ extern "C" DES_API int des_session_eval(des_session *s) {
     DES_SESSION(s);
     if (s->n_local < s->N) DES_CUDA(cudaMemsetAsync(s->fitness_all, 0, s->N * sizeof(float), s->stream));
     return des_nes_eval(s->fitness_all + s->member_offset, s->theta, s->obs, s->target, s->dims, s->opt.sigma, s->clip,
-                        s->seed, 0, s->state, s->member_offset, s->n_local, s->precision, s->stream);
+                        s->seed, 0, s->state, s->member_offset, s->n_local, s->precision, s->eval_ws, s->eval_ws_bytes,
+                        s->stream);
 }
 
 extern "C" DES_API int des_session_rank_and_grad(des_session *s) {

@@ -128,6 +128,32 @@ __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float &z0, 
     z1 = nr * sin_approx(ang);
 }
 
+// Box-Muller in parts, for consumers that fold a scale into the radius: the pair is (nr*c, nr*s) with
+// nr = -sqrt(scale2 * -2 ln u1) = -scale*sqrt(-2 ln u1) for scale2 = scale^2 (pass kNeg2Ln2 * scale^2).
+constexpr float kNeg2Ln2 = -1.3862943611198906f;
+struct BmParts {
+    float nr, c, s;
+};
+__device__ __forceinline__ BmParts box_muller_parts(uint32_t xa, uint32_t xb, float neg2ln2_scale2) {
+    BmParts p;
+    const float u1 = u32_to_one_two(xa) - 0.99999994039535522f;
+    p.nr = -sqrt_approx(neg2ln2_scale2 * lg2_approx(u1));
+    const float ang = __fmaf_rn(u32_to_one_two(xb), kTwoPiF, -kAngOffF);
+    p.c = cos_approx(ang);
+    p.s = sin_approx(ang);
+    return p;
+}
+// out[e] = base[e] + scale * eps[e] for the four parameters of quad q (scale folded into the radius:
+// differs from fma(scale, eps, base) by <= 1 ulp of scale*eps).
+__device__ __forceinline__ float4 perturbed_quad(uint32_t q, uint32_t member, uint32_t gen, uint32_t tag,
+                                                 const PhiloxKey &key, float neg2ln2_scale2, float4 base) {
+    const uint4 x = philox4x32_10(q, member, gen, tag, key);
+    const BmParts a = box_muller_parts(x.x, x.y, neg2ln2_scale2);
+    const BmParts b = box_muller_parts(x.z, x.w, neg2ln2_scale2);
+    return make_float4(__fmaf_rn(a.nr, a.c, base.x), __fmaf_rn(a.nr, a.s, base.y), __fmaf_rn(b.nr, b.c, base.z),
+                       __fmaf_rn(b.nr, b.s, base.w));
+}
+
 // The four normals of quad q of `member` at `gen`.
 __device__ __forceinline__ float4 noise_quad(uint32_t q, uint32_t member, uint32_t gen, uint32_t tag,
                                              const PhiloxKey &key) {

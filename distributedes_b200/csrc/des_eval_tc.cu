@@ -51,7 +51,7 @@ struct TcCfg {
     static constexpr int SLOT_COLS = ACOLS + 2 * kNC;         // + two accumulator stages
     static constexpr int SLOT_BYTES = (X3 ? 2 : 1) * 64 * 128;   // one B tile: 64 rows x 128 B (hi [+ lo])
     static constexpr int X_TILE_BYTES = (X3 ? 2 : 1) * 128 * 128;   // one X tile: 128 rows x 128 B (hi [+ lo])
-    static constexpr int SMALL_FLOATS = 2 * H + kMaxA * H + kMaxA;   // b1, b2, W3'^T [H][8], b3[8]
+    static constexpr int SMALL_FLOATS = 2 * H + kMaxA * H + kMaxA;   // b1, b2, W3' [8][H], b3[8]
     static constexpr int NT_MAX = 512 / SLOT_COLS >= 2 ? 2 : 1;     // tile slots resident in TMEM at once
 };
 
@@ -61,11 +61,12 @@ struct TcArgs {
     const des_state *state;
     Layout L;
     int T, n_tiles, n_pass, n_slots;
-    float sigma, clip;
+    float sigma, clip, neg2ln2_sigma2;
     PhiloxKey key;
     uint32_t gen;
     uint64_t member_offset;
     int64_t n_local;
+    uint8_t *cache;        // optional per-CTA image of one member's weight tiles (multi-pass shapes), else NULL
 };
 
 // barrier block in shared memory
@@ -101,7 +102,7 @@ __device__ __forceinline__ float perturbed1(const float *__restrict__ theta, int
 }
 
 template <bool X3>
-__device__ __forceinline__ void store_octet(uint8_t *slot, int r, int c8, const float (&w)[8]) {
+__device__ __forceinline__ void store_octet(uint8_t *slot, uint8_t *mirror, int r, int c8, const float (&w)[8]) {
     uint4 hi, lo;
     if (X3) {
         split_h2(w[0], w[1], hi.x, lo.x); split_h2(w[2], w[3], hi.y, lo.y);
@@ -110,6 +111,23 @@ __device__ __forceinline__ void store_octet(uint8_t *slot, int r, int c8, const 
         hi.x = pack_h2(w[0], w[1]); hi.y = pack_h2(w[2], w[3]); hi.z = pack_h2(w[4], w[5]); hi.w = pack_h2(w[6], w[7]);
     }
     const int off = r * 128 + ((c8 ^ (r & 7)) << 4);          // SWIZZLE_128B
+    *reinterpret_cast<uint4 *>(slot + off) = hi;
+    if (X3) *reinterpret_cast<uint4 *>(slot + 8192 + off) = lo;
+    if (mirror) {       // same thread re-reads exactly these bytes in the later passes (no cross-thread ordering needed)
+        *reinterpret_cast<uint4 *>(mirror + off) = hi;
+        if (X3) *reinterpret_cast<uint4 *>(mirror + 8192 + off) = lo;
+    }
+}
+// later passes over the same member: copy this thread's chunk(s) of the cached tile image back into the ring slot
+template <bool X3>
+__device__ __forceinline__ void load_octet(uint4 &hi, uint4 &lo, const uint8_t *mirror, int r, int c8) {
+    const int off = r * 128 + ((c8 ^ (r & 7)) << 4);
+    hi = *reinterpret_cast<const uint4 *>(mirror + off);
+    if (X3) lo = *reinterpret_cast<const uint4 *>(mirror + 8192 + off);
+}
+template <bool X3>
+__device__ __forceinline__ void put_octet(uint8_t *slot, int r, int c8, const uint4 &hi, const uint4 &lo) {
+    const int off = r * 128 + ((c8 ^ (r & 7)) << 4);
     *reinterpret_cast<uint4 *>(slot + off) = hi;
     if (X3) *reinterpret_cast<uint4 *>(slot + 8192 + off) = lo;
 }
@@ -199,15 +217,15 @@ __global__ void __launch_bounds__((4 * NT + kGenWarps + 1) * 32, 1) eval_tc_kern
         // =================================== MMA issuer (one thread) ===================================
         if (lane == 0) {
             constexpr uint32_t idesc = idesc_f16(128, kNC);
-            uint32_t slot_c = 0;                 // ring consume counter
+            uint32_t rs = 0, rph = 0;            // ring cursor: slot index and phase
             uint32_t acc_u[2] = {0, 0};          // accumulator-stage use counters per tile slot
             uint32_t hv[2] = {0, 0};             // (member, pass) counter per tile slot for h_ready
             for (int64_t m = first; m < a.n_local; m += stride) {
                 for (int pass = 0; pass < a.n_pass; ++pass) {
                     // ---- layer 1: D1 chunk nc = X W1'[64nc:64nc+64, :]^T
                     for (int nc = 0; nc < C::NCH; ++nc) {
-                        const uint32_t s = slot_c % a.n_slots, sph = (slot_c / a.n_slots) & 1;
-                        ++slot_c;
+                        const uint32_t s = rs, sph = rph;
+                        if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
                         mbar_wait(smem_u32(&bars->slot_full[s]), sph);
                         tc_fence_after();
                         const uint32_t bbase = smem_u32(ring + (size_t)s * C::SLOT_BYTES);
@@ -245,8 +263,8 @@ __global__ void __launch_bounds__((4 * NT + kGenWarps + 1) * 32, 1) eval_tc_kern
                         }
                         tc_fence_after();
                         for (int ka = 0; ka < C::KAT; ++ka) {
-                            const uint32_t s = slot_c % a.n_slots, sph = (slot_c / a.n_slots) & 1;
-                            ++slot_c;
+                            const uint32_t s = rs, sph = rph;
+                            if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
                             mbar_wait(smem_u32(&bars->slot_full[s]), sph);
                             tc_fence_after();
                             const uint32_t bbase = smem_u32(ring + (size_t)s * C::SLOT_BYTES);
@@ -312,16 +330,25 @@ __global__ void __launch_bounds__((4 * NT + kGenWarps + 1) * 32, 1) eval_tc_kern
                             tc_fence_after();
                         }
                         uint32_t hi[16], lo[16];
-                        const float4 *bq = reinterpret_cast<const float4 *>(b1 + nc * kNC + half * 32);
+                        if (X3) {
+                            const float4 *bq = reinterpret_cast<const float4 *>(b1 + nc * kNC + half * 32);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 b = bq[i];
-                            const float x0 = __uint_as_float(v[4 * i]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
-                            const float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
-                            if (X3) {
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 b = bq[i];
+                                const float x0 = __uint_as_float(v[4 * i]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
+                                const float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
                                 split_h2(tanh_acc(x0), tanh_acc(x1), hi[2 * i], lo[2 * i]);
                                 split_h2(tanh_acc(x2), tanh_acc(x3), hi[2 * i + 1], lo[2 * i + 1]);
-                            } else {
+                            }
+                        } else {
+                            // (tanh.approx.f16x2 was tried here: SASS issues one MUFU.TANH.F16 per half plus a PRMT,
+                            //  so it saves nothing over fp32 MUFU.TANH and costs precision)
+                            const float4 *bq = reinterpret_cast<const float4 *>(b1 + nc * kNC + half * 32);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 b = bq[i];
+                                const float x0 = __uint_as_float(v[4 * i]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
+                                const float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
                                 hi[2 * i] = pack_h2(tanh_fast(x0), tanh_fast(x1));
                                 hi[2 * i + 1] = pack_h2(tanh_fast(x2), tanh_fast(x3));
                             }
@@ -336,9 +363,9 @@ __global__ void __launch_bounds__((4 * NT + kGenWarps + 1) * 32, 1) eval_tc_kern
                 if (lane == 0) mbar_arrive(smem_u32(&bars->h_ready[ts]));
                 ++hv;
                 // ---------------- epilogue 2+3: H2 = tanh(D2 + b2); a = H2 W3^T + b3 in fp32 registers
-                float act[kMaxA];
+                float2 actp[kMaxA];                          // (even-n, odd-n) partial sums of action q
 #pragma unroll
-                for (int q = 0; q < kMaxA; ++q) act[q] = 0.f;
+                for (int q = 0; q < kMaxA; ++q) actp[q] = make_float2(0.f, 0.f);
                 for (int nc = 0; nc < C::NCH; ++nc) {
                     const uint32_t u = acc_u++, st = u & 1, ph = (u >> 1) & 1;
                     mbar_wait(smem_u32(&bars->acc_full[ts][st]), ph);
@@ -358,29 +385,25 @@ __global__ void __launch_bounds__((4 * NT + kGenWarps + 1) * 32, 1) eval_tc_kern
 #pragma unroll
                         for (int i4 = 0; i4 < 8; ++i4) {
                             const float4 b = bq[i4];
-                            const float bb[4] = {b.x, b.y, b.z, b.w};
+                            const float x0 = __uint_as_float(v[4 * i4]) + b.x, x1 = __uint_as_float(v[4 * i4 + 1]) + b.y;
+                            const float x2 = __uint_as_float(v[4 * i4 + 2]) + b.z, x3 = __uint_as_float(v[4 * i4 + 3]) + b.w;
+                            const float2 h01 = X3 ? make_float2(tanh_acc(x0), tanh_acc(x1)) : make_float2(tanh_fast(x0), tanh_fast(x1));
+                            const float2 h23 = X3 ? make_float2(tanh_acc(x2), tanh_acc(x3)) : make_float2(tanh_fast(x2), tanh_fast(x3));
+                            // layer 3 (model.py:38) in fp32 on packed FFMA2: W3' row-major [q][n], 4 consecutive n per LDS.128
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int i = 4 * i4 + e;
-                                const float x = __uint_as_float(v[i]) + bb[e];
-                                const float h = X3 ? tanh_acc(x) : tanh_fast(x);
-                                // layer 3 (model.py:38) in fp32: W3' stored transposed [n][8] -> one or two LDS.128
-                                const float4 wa = *reinterpret_cast<const float4 *>(w3 + (n0 + i) * kMaxA);
-                                act[0] = __fmaf_rn(h, wa.x, act[0]);
-                                act[1] = __fmaf_rn(h, wa.y, act[1]);
-                                act[2] = __fmaf_rn(h, wa.z, act[2]);
-                                act[3] = __fmaf_rn(h, wa.w, act[3]);
-                                if (L.A > 4) {
-                                    const float4 wb = *reinterpret_cast<const float4 *>(w3 + (n0 + i) * kMaxA + 4);
-                                    act[4] = __fmaf_rn(h, wb.x, act[4]);
-                                    act[5] = __fmaf_rn(h, wb.y, act[5]);
-                                    act[6] = __fmaf_rn(h, wb.z, act[6]);
-                                    act[7] = __fmaf_rn(h, wb.w, act[7]);
+                            for (int q = 0; q < kMaxA; ++q) {
+                                if (q < 4 || L.A > 4) {
+                                    const float4 w = *reinterpret_cast<const float4 *>(w3 + q * H + n0 + 4 * i4);
+                                    actp[q] = ffma2(h01, make_float2(w.x, w.y), actp[q]);
+                                    actp[q] = ffma2(h23, make_float2(w.z, w.w), actp[q]);
                                 }
                             }
                         }
                     }
                 }
+                float act[kMaxA];
+#pragma unroll
+                for (int q = 0; q < kMaxA; ++q) act[q] = actp[q].x + actp[q].y;
                 const int t = (pass * NT + ts) * 128 + row;
 #pragma unroll
                 for (int q = 0; q < kMaxA; ++q) {
@@ -410,7 +433,10 @@ __global__ void __launch_bounds__((4 * NT + kGenWarps + 1) * 32, 1) eval_tc_kern
         // =================================== weight generators =========================================
         if (NT == 2) reg_dealloc<56>();
         const int gtid = threadIdx.x - kEpiWarps * 32;                  // 0..511
-        uint32_t slot_p = 0, mi = 0;
+        uint32_t rs = 0, rph = 0, mi = 0;     // ring cursor: slot index and phase
+        constexpr int kSlotsPerMember = C::NCH + C::NCH * C::KAT;
+        uint8_t *const cache = (a.cache && a.n_pass > 1)
+                                   ? a.cache + (size_t)blockIdx.x * kSlotsPerMember * C::SLOT_BYTES : nullptr;
         // theta of this thread's W2 octet is prefetched one ring slot ahead (it does not depend on the member)
         const int r2 = gtid >> 3, c82 = gtid & 7;
         auto w2_index = [&](int nc, int ka) { return L.off_w2 + (nc * 64 + r2) * H + ka * 64 + c82 * 8; };
@@ -423,28 +449,19 @@ __global__ void __launch_bounds__((4 * NT + kGenWarps + 1) * 32, 1) eval_tc_kern
             float *sm = small + p * C::SMALL_FLOATS;
             mbar_wait(smem_u32(&bars->small_empty[p]), ((mi >> 1) & 1) ^ 1);
             for (int i = gtid; i < H / 4; i += kGenThreads) {                // b1, b2: aligned quads
-                const float4 z1 = noise_quad((uint32_t)((L.off_b1 >> 2) + i), member, gen, kStreamNesEps, a.key);
-                const float4 t1 = __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_b1) + i);
-                reinterpret_cast<float4 *>(sm)[i] = make_float4(__fmaf_rn(a.sigma, z1.x, t1.x), __fmaf_rn(a.sigma, z1.y, t1.y),
-                                                                __fmaf_rn(a.sigma, z1.z, t1.z), __fmaf_rn(a.sigma, z1.w, t1.w));
-                const float4 z2 = noise_quad((uint32_t)((L.off_b2 >> 2) + i), member, gen, kStreamNesEps, a.key);
-                const float4 t2 = __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_b2) + i);
-                reinterpret_cast<float4 *>(sm + H)[i] = make_float4(__fmaf_rn(a.sigma, z2.x, t2.x), __fmaf_rn(a.sigma, z2.y, t2.y),
-                                                                    __fmaf_rn(a.sigma, z2.z, t2.z), __fmaf_rn(a.sigma, z2.w, t2.w));
+                const float4 v1 = perturbed_quad((uint32_t)((L.off_b1 >> 2) + i), member, gen, kStreamNesEps, a.key,
+                                                 a.neg2ln2_sigma2, __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_b1) + i));
+                reinterpret_cast<float4 *>(sm)[i] = v1;
+                reinterpret_cast<float4 *>(sm + H)[i] =
+                    perturbed_quad((uint32_t)((L.off_b2 >> 2) + i), member, gen, kStreamNesEps, a.key, a.neg2ln2_sigma2,
+                                   __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_b2) + i));
             }
-            for (int i = gtid; i < L.A * H / 4; i += kGenThreads) {          // W3' rows are H floats: aligned quads
-                const float4 z = noise_quad((uint32_t)((L.off_w3 >> 2) + i), member, gen, kStreamNesEps, a.key);
-                const float4 t = __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_w3) + i);
-                const int q = (4 * i) / H, n = (4 * i) - q * H;               // stored transposed: w3t[n][q]
-                float *dst = sm + 2 * H + n * kMaxA + q;
-                dst[0] = __fmaf_rn(a.sigma, z.x, t.x);
-                dst[kMaxA] = __fmaf_rn(a.sigma, z.y, t.y);
-                dst[2 * kMaxA] = __fmaf_rn(a.sigma, z.z, t.z);
-                dst[3 * kMaxA] = __fmaf_rn(a.sigma, z.w, t.w);
-            }
-            if (mi < 2)                                                       // unused action columns stay zero (finite)
-                for (int i = gtid; i < H * kMaxA; i += kGenThreads)
-                    if ((i & (kMaxA - 1)) >= L.A) sm[2 * H + i] = 0.f;
+            for (int i = gtid; i < L.A * H / 4; i += kGenThreads)            // W3' [q][n] row-major: aligned quads
+                reinterpret_cast<float4 *>(sm + 2 * H)[i] =
+                    perturbed_quad((uint32_t)((L.off_w3 >> 2) + i), member, gen, kStreamNesEps, a.key, a.neg2ln2_sigma2,
+                                   __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_w3) + i));
+            if (mi < 2)                                                       // unused action rows stay zero (finite)
+                for (int i = L.A * H + gtid; i < H * kMaxA; i += kGenThreads) sm[2 * H + i] = 0.f;
             if (gtid < L.A) sm[2 * H + kMaxA * H + gtid] = perturbed1(a.theta, L.off_b3 + gtid, a.sigma, member, gen, a.key);
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars->small_full[p]));
@@ -452,11 +469,16 @@ __global__ void __launch_bounds__((4 * NT + kGenWarps + 1) * 32, 1) eval_tc_kern
             for (int pass = 0; pass < a.n_pass; ++pass) {
                 // ---- layer-1 tiles: rows [64nc, 64nc+64) of W1', k < d0 (zero padded to 32)
                 for (int nc = 0; nc < C::NCH; ++nc) {
-                    const uint32_t s = slot_p % a.n_slots, sph = (slot_p / a.n_slots) & 1;
-                    ++slot_p;
+                    const uint32_t s = rs, sph = rph;
+                    if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
                     mbar_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
                     uint8_t *slot = ring + (size_t)s * C::SLOT_BYTES;
-                    if (gtid < 256) {   // 64 rows x 4 octets = 256 items
+                    uint8_t *mirror = cache ? cache + (size_t)nc * C::SLOT_BYTES : nullptr;
+                    if (gtid < 256 && pass > 0 && cache) {
+                        uint4 hi, lo;
+                        load_octet<X3>(hi, lo, mirror, gtid >> 2, gtid & 3);
+                        put_octet<X3>(slot, gtid >> 2, gtid & 3, hi, lo);
+                    } else if (gtid < 256) {   // 64 rows x 4 octets = 256 items
                         const int r = gtid >> 2, c8 = gtid & 3;
                         const int n = nc * 64 + r;
                         float w[8];
@@ -467,10 +489,8 @@ __global__ void __launch_bounds__((4 * NT + kGenWarps + 1) * 32, 1) eval_tc_kern
                                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                                 if (k < L.d0) {
                                     const int j = L.off_w1 + n * L.d0 + k;
-                                    const float4 z = noise_quad((uint32_t)(j >> 2), member, gen, kStreamNesEps, a.key);
-                                    const float4 t = __ldg(reinterpret_cast<const float4 *>(a.theta + j));
-                                    v = make_float4(__fmaf_rn(a.sigma, z.x, t.x), __fmaf_rn(a.sigma, z.y, t.y),
-                                                    __fmaf_rn(a.sigma, z.z, t.z), __fmaf_rn(a.sigma, z.w, t.w));
+                                    v = perturbed_quad((uint32_t)(j >> 2), member, gen, kStreamNesEps, a.key, a.neg2ln2_sigma2,
+                                                       __ldg(reinterpret_cast<const float4 *>(a.theta + j)));
                                 }
                                 w[4 * hq] = v.x; w[4 * hq + 1] = v.y; w[4 * hq + 2] = v.z; w[4 * hq + 3] = v.w;
                             }
@@ -481,7 +501,7 @@ __global__ void __launch_bounds__((4 * NT + kGenWarps + 1) * 32, 1) eval_tc_kern
                                 w[e] = (k < L.d0) ? perturbed1(a.theta, L.off_w1 + n * L.d0 + k, a.sigma, member, gen, a.key) : 0.f;
                             }
                         }
-                        store_octet<X3>(slot, r, c8, w);
+                        store_octet<X3>(slot, mirror, r, c8, w);
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
@@ -490,25 +510,29 @@ __global__ void __launch_bounds__((4 * NT + kGenWarps + 1) * 32, 1) eval_tc_kern
                 // ---- layer-2 tiles: rows [64nc, +64) x k [64ka, +64) of W2'
                 for (int nc = 0; nc < C::NCH; ++nc) {
                     for (int ka = 0; ka < C::KAT; ++ka) {
-                        const uint32_t s = slot_p % a.n_slots, sph = (slot_p / a.n_slots) & 1;
-                        ++slot_p;
+                        const uint32_t s = rs, sph = rph;
+                        if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
                         uint8_t *slot = ring + (size_t)s * C::SLOT_BYTES;
-                        {   // 64 rows x 8 octets = 512 items: one per thread
+                        uint8_t *mirror = cache ? cache + (size_t)(C::NCH + nc * C::KAT + ka) * C::SLOT_BYTES : nullptr;
+                        if (pass > 0 && cache) {
+                            uint4 hi, lo;                                     // issued before the ring wait: L2 latency overlaps it
+                            load_octet<X3>(hi, lo, mirror, r2, c82);
+                            mbar_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
+                            put_octet<X3>(slot, r2, c82, hi, lo);
+                        } else {   // 64 rows x 8 octets = 512 items: one per thread
                             const float4 t0 = tn0, t1 = tn1;
                             int nnc = nc, nka = ka + 1;                       // next slot (wraps to the next member)
                             if (nka == C::KAT) { nka = 0; if (++nnc == C::NCH) nnc = 0; }
                             tn0 = __ldg(reinterpret_cast<const float4 *>(a.theta + w2_index(nnc, nka)));
                             tn1 = __ldg(reinterpret_cast<const float4 *>(a.theta + w2_index(nnc, nka) + 4));
                             const int j0 = w2_index(nc, ka);
-                            const float4 z0 = noise_quad((uint32_t)(j0 >> 2), member, gen, kStreamNesEps, a.key);
-                            const float4 z1 = noise_quad((uint32_t)(j0 >> 2) + 1, member, gen, kStreamNesEps, a.key);
-                            float w[8];
-                            w[0] = __fmaf_rn(a.sigma, z0.x, t0.x); w[1] = __fmaf_rn(a.sigma, z0.y, t0.y);
-                            w[2] = __fmaf_rn(a.sigma, z0.z, t0.z); w[3] = __fmaf_rn(a.sigma, z0.w, t0.w);
-                            w[4] = __fmaf_rn(a.sigma, z1.x, t1.x); w[5] = __fmaf_rn(a.sigma, z1.y, t1.y);
-                            w[6] = __fmaf_rn(a.sigma, z1.z, t1.z); w[7] = __fmaf_rn(a.sigma, z1.w, t1.w);
+                            const float4 w0 = perturbed_quad((uint32_t)(j0 >> 2), member, gen, kStreamNesEps, a.key,
+                                                             a.neg2ln2_sigma2, t0);
+                            const float4 w1 = perturbed_quad((uint32_t)(j0 >> 2) + 1, member, gen, kStreamNesEps, a.key,
+                                                             a.neg2ln2_sigma2, t1);
+                            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
                             mbar_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
-                            store_octet<X3>(slot, r2, c82, w);
+                            store_octet<X3>(slot, mirror, r2, c82, w);
                         }
                         fence_proxy_async_smem();
                         __syncwarp();
@@ -558,9 +582,34 @@ static int launch_tc(TcArgs &a, cudaStream_t st) {
     return launch_tc_nt<H, MODE, 1>(a, st);
 }
 
+static void tc_shape(int H, bool x3, int T, int &n_pass, size_t &slot_bytes, int &slots_per_member) {
+    const int nch = H / kNC, acols = x3 ? H : H / 2;
+    const int nt_max = 512 / (acols + 2 * kNC) >= 2 ? 2 : 1;
+    const int n_tiles = T / 128;
+    n_pass = (nt_max >= 2 && n_tiles % 2 == 0) ? n_tiles / 2 : n_tiles;
+    slot_bytes = (size_t)(x3 ? 2 : 1) * 64 * 128;
+    slots_per_member = nch + nch * (H / 64);
+}
+
+size_t eval_tc_workspace_bytes(des_dims dims, int precision) {
+    const int H = dims.hidden;
+    if (!(H == 64 || H == 128 || H == 256) || dims.tape_len % 128 != 0) return 0;
+    int n_pass, spm;
+    size_t sb;
+    tc_shape(H, precision == DES_FWD_F16X3, dims.tape_len, n_pass, sb, spm);
+    if (n_pass <= 1) return 0;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+        cudaGetLastError();
+        sms = 148;
+    }
+    return (size_t)sms * spm * sb;
+}
+
 int eval_tc_launch(float *fitness, const float *theta, const float *obs, const float *target, des_dims dims,
                    double sigma, double clip, uint64_t seed, uint64_t generation, const des_state *state,
-                   int64_t member_offset, int64_t n_local, int precision, cudaStream_t st) {
+                   int64_t member_offset, int64_t n_local, int precision, void *workspace, size_t workspace_bytes,
+                   cudaStream_t st) {
     const int H = dims.hidden;
     if (!(H == 64 || H == 128 || H == 256) || dims.state_dim > kK1 || dims.action_dim > kMaxA || dims.tape_len % 128 != 0) {
         set_error("des_nes_eval(tensor): needs hidden in {64,128,256}, state_dim <= %d, action_dim <= %d, tape_len %% 128 == 0 "
@@ -577,9 +626,14 @@ int eval_tc_launch(float *fitness, const float *theta, const float *obs, const f
     a.L = Layout(dims.state_dim, H, dims.action_dim);
     a.T = dims.tape_len;
     a.sigma = (float)sigma; a.clip = (float)clip;
+    a.neg2ln2_sigma2 = kNeg2Ln2 * (float)sigma * (float)sigma;
     a.key = make_philox_key(seed); a.gen = (uint32_t)generation;
     a.member_offset = (uint64_t)member_offset; a.n_local = n_local;
     const bool x3 = precision == DES_FWD_F16X3;
+    // multi-pass shapes: with a workspace, the tiles generated in pass 0 are mirrored to it and copied back in the
+    // later passes (L2-resident, 148 x ~320 KB); without one they are regenerated per pass (slower, same results)
+    const size_t need = eval_tc_workspace_bytes(dims, precision);
+    a.cache = (need > 0 && workspace && workspace_bytes >= need && ((uintptr_t)workspace & 15) == 0) ? (uint8_t *)workspace : nullptr;
     switch (H) {
         case 64: return x3 ? launch_tc<64, DES_FWD_F16X3>(a, st) : launch_tc<64, DES_FWD_F16>(a, st);
         case 128: return x3 ? launch_tc<128, DES_FWD_F16X3>(a, st) : launch_tc<128, DES_FWD_F16>(a, st);

@@ -57,11 +57,14 @@ __global__ void __launch_bounds__(kGradThreads) grad_chunk_kernel(float *__restr
 #pragma unroll 2
     for (int64_t i = i0; i < i1; ++i) {
         const float s = __ldg(shaped + i);     // warp-uniform broadcast load
-        const float4 z = noise_quad((uint32_t)q, (uint32_t)(member_offset + i), gen, kStreamNesEps, key);
-        acc.x = __fmaf_rn(s, z.x, acc.x);
-        acc.y = __fmaf_rn(s, z.y, acc.y);
-        acc.z = __fmaf_rn(s, z.z, acc.z);
-        acc.w = __fmaf_rn(s, z.w, acc.w);
+        const uint4 x = philox4x32_10((uint32_t)q, (uint32_t)(member_offset + i), gen, kStreamNesEps, key);
+        const BmParts a = box_muller_parts(x.x, x.y, kNeg2Ln2);
+        const BmParts b = box_muller_parts(x.z, x.w, kNeg2Ln2);
+        const float as = a.nr * s, bs = b.nr * s;                 // s_i * radius: one multiply per pair
+        acc.x = __fmaf_rn(as, a.c, acc.x);
+        acc.y = __fmaf_rn(as, a.s, acc.y);
+        acc.z = __fmaf_rn(bs, b.c, acc.z);
+        acc.w = __fmaf_rn(bs, b.s, acc.w);
     }
     *reinterpret_cast<float4 *>(ws + (int64_t)blockIdx.y * Ppad + 4 * q) = acc;
 }

@@ -70,9 +70,12 @@ class NESEngine:
         self.rank_ws = self.k.rank_workspace(self.n_local, dev)
         self.grad_ws = self.k.grad_workspace(self.n_local, self.P, dev)
         self.set_tape(obs, target)
+        self.eval_ws = (self.k.eval_workspace(self.d0, self.H, self.A, self.T, precision, dev)
+                        if hasattr(self.k, 'eval_workspace') else None)
         self.generation_index = 0
         self._graph = None
-        self._use_graph = bool(use_graph) and self.world == 1 and self.device.type == 'cuda'
+        # NCCL collectives are capturable (torch >= 2.x, NCCL >= 2.9): the graph then holds kernels AND collectives
+        self._use_graph = bool(use_graph) and self.device.type == 'cuda'
 
     # -- inputs ------------------------------------------------------------------------------------------
     def set_tape(self, obs, target):
@@ -98,7 +101,8 @@ class NESEngine:
         if self.n_local:
             self.k.nes_eval(self.theta, self.obs, self.target, hidden=self.H, sigma=self.sigma, clip=self.clip,
                             seed=self.seed, state=self.state, member_offset=self.offset, n_local=self.n_local,
-                            precision=self.precision, out=self.fitness_all[self.offset:self.offset + self.n_local])
+                            precision=self.precision, out=self.fitness_all[self.offset:self.offset + self.n_local],
+                            workspace=self.eval_ws)
         if self.world > 1:
             dist.all_reduce(self.fitness_all, group=self.pg)
         return self.fitness_all

@@ -96,8 +96,15 @@ def nes_perturb(theta, n_members, sigma, seed, generation, member_offset=0):
     return out
 
 
+def eval_workspace(state_dim, hidden, action_dim, tape_len, precision, device):
+    """Optional scratch for des_nes_eval (multi-pass tensor-core shapes); None when the shape needs none."""
+    with torch.cuda.device(device):
+        nbytes = _lib.load().des_nes_eval_workspace_bytes(Dims(state_dim, hidden, action_dim, tape_len), _precision(precision))
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device) if nbytes else None
+
+
 def nes_eval(theta, obs, target, *, hidden, sigma, clip, seed, generation=0, state=None, member_offset=0,
-             n_local, precision='fp32', out=None):
+             n_local, precision='fp32', out=None, workspace=None):
     """Fused sample+forward+fitness for members [member_offset, member_offset+n_local) -> fitness[n_local]."""
     T, d0 = obs.shape
     A = target.shape[1]
@@ -115,6 +122,7 @@ def nes_eval(theta, obs, target, *, hidden, sigma, clip, seed, generation=0, sta
             _ptr(out, torch.float32, 'out'), _ptr(theta, torch.float32, 'theta'), _ptr(obs, torch.float32, 'obs'),
             _ptr(target, torch.float32, 'target'), Dims(d0, hidden, A, T), sigma, clip, seed, generation,
             _ptr(state, torch.uint8, 'state', allow_none=True), member_offset, n_local, _precision(precision),
+            _ptr(workspace, torch.uint8, 'workspace', allow_none=True), workspace.numel() if workspace is not None else 0,
             _stream()), 'des_nes_eval')
     return out
 

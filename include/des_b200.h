@@ -114,11 +114,16 @@ DES_API int des_nes_perturb(float *theta_out_dev, const float *theta_dev, int64_
  * model.py:34-39 over the synthetic tape env (obs_dev [T][d0], target_dev [T][A], both fp32).
  * `state_dev` may be NULL (then `generation` is used); if non-NULL, state_dev->generation wins
  * (graph replay).  precision: see des_precision; DES_FWD_F16 / F16X3 need H in {64,128,256},
- * d0 <= 32, A <= 8, T a multiple of 128 and |values| < 65504 — otherwise DES_ERR_UNSUPPORTED (never a silent fallback). */
+ * d0 <= 32, A <= 8, T a multiple of 128 and |values| < 65504 — otherwise DES_ERR_UNSUPPORTED (never a silent fallback).
+ * workspace (optional, may be NULL): des_nes_eval_workspace_bytes() bytes, 16-byte aligned; shapes whose tape does not
+ * fit the tensor memory in one pass use it to keep a member's generated weight tiles between passes instead of
+ * regenerating them (same results either way). */
+DES_API size_t des_nes_eval_workspace_bytes(des_dims dims, int precision);
 DES_API int des_nes_eval(float *fitness_out_dev, const float *theta_dev, const float *obs_dev,
                  const float *target_dev, des_dims dims, double sigma, double clip, uint64_t seed,
                  uint64_t generation, const des_state *state_dev, int64_t member_offset,
-                 int64_t n_local, int precision, void *stream);
+                 int64_t n_local, int precision, void *workspace_dev, size_t workspace_bytes,
+                 void *stream);
 
 /* ---- centered-rank shaping ------------------------------------------------------------------ */
 

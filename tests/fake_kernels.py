@@ -31,7 +31,7 @@ def grad_workspace(n_local, P, device):
 
 
 def nes_eval(theta, obs, target, *, hidden, sigma, clip, seed, generation=0, state=None, member_offset=0, n_local,
-             precision='fp32', out=None):
+             precision='fp32', out=None, workspace=None):
     gen = int(state[0]) if state is not None else generation
     T, d0 = obs.shape
     A = target.shape[1]

@@ -70,9 +70,9 @@ def test_argument_validation_precedes_cuda(lib):
     from distributedes_b200 import _lib
     rc = lib.des_centered_rank(None, None, None, 1, 0, 1, None, 0, None)
     assert rc == -1 and b'N >= 2' in lib.des_last_error()
-    rc = lib.des_nes_eval(None, None, None, None, _lib.Dims(0, 64, 1, 8), 0.1, 1.0, 0, 0, None, 0, 1, 0, None)
+    rc = lib.des_nes_eval(None, None, None, None, _lib.Dims(0, 64, 1, 8), 0.1, 1.0, 0, 0, None, 0, 1, 0, None, 0, None)
     assert rc == -1 and b'bad dims' in lib.des_last_error()
-    rc = lib.des_nes_eval(None, None, None, None, _lib.Dims(3, 64, 1, 8), 0.1, 1.0, 0, 0, None, 0, 1, 0, None)
+    rc = lib.des_nes_eval(None, None, None, None, _lib.Dims(3, 64, 1, 8), 0.1, 1.0, 0, 0, None, 0, 1, 0, None, 0, None)
     assert rc == -1 and b'NULL' in lib.des_last_error()
     rc = lib.des_nes_grad_partial(None, None, 4, 10, 0, 0, None, 0, None, 0, None)
     assert rc == -1

@@ -17,7 +17,7 @@ def both_norms(got, ref, tol=1e-5):
     assert np.max(np.abs(got - ref)) <= tol * np.max(np.abs(ref))
 
 
-@pytest.mark.parametrize('n,lam', [(1024, 256), (257, 37), (64, 5), (130, 200), (3000, 64)])
+@pytest.mark.parametrize('n,lam', [(1024, 256), (257, 37), (64, 5), (130, 200), (3000, 64), (4096, 1024)])
 def test_rank_mu_matches_restatement(n, lam):
     from distributedes_b200 import ops
     rs = np.random.RandomState(n + lam)
@@ -56,3 +56,20 @@ def test_rank_mu_shards_sum_to_whole_and_active_weights():
     both_norms(sum(p.cpu().numpy().astype(np.float64) for p in parts), ref)
     empty = ops.cma_rank_mu(Yt[:0].contiguous(), wt[:0].contiguous())
     assert float(empty.abs().max()) == 0.0
+
+
+def test_rank_mu_eight_shards_of_baseline_config5():
+    """BASELINE configs[4]: n=4096, lambda=1024 split over 8 shards of 128 members; the all-reduce contract is
+    sum(partials) == whole, checked here on one GPU by summing the eight partials in fp32 like NCCL would."""
+    from distributedes_b200 import ops
+    n, lam = 4096, 1024
+    rs = np.random.RandomState(8)
+    k = cma.cma_constants(n, lam)
+    Y = rs.randn(lam, n)
+    ref = cma.rank_mu_delta(Y, k['w'])
+    Yt = torch.from_numpy(Y.astype(np.float32)).to(DEV)
+    wt = torch.from_numpy(k['w'].astype(np.float32)).to(DEV)
+    total = torch.zeros((n, n), dtype=torch.float32, device=DEV)
+    for r in range(8):
+        total += ops.cma_rank_mu(Yt[r * 128:(r + 1) * 128].contiguous(), wt[r * 128:(r + 1) * 128].contiguous())
+    both_norms(total.cpu().numpy(), ref)

@@ -1,0 +1,61 @@
+"""Two real GPUs, NCCL: the sharded generation equals the single-GPU generation bit for bit in fitness and to
+fp32 summation order in the update.  Skipped on a one-GPU box (the CPU gloo test covers the host logic there)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, N, precision, use_graph, ret):
+    sys.path.insert(0, REPO)
+    from distributedes_b200.engine import NESEngine
+    from oracle import nes_oracle as orc
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world,
+                            device_id=torch.device('cuda', rank))
+    try:
+        d0, H, A, T = 24, 64, 4, 256
+        obs, target = orc.synthetic_tape(T, d0, A)
+        eng = NESEngine(state_dim=d0, hidden=H, action_dim=A, pop_size=N, theta0=orc.synthetic_theta(d0, H, A), obs=obs,
+                        target=target, sigma=0.1, learning_rate=0.1, clip=1.0, seed=21, precision=precision,
+                        device='cuda:%d' % rank, use_graph=use_graph)
+        for _ in range(3):
+            eng.generation()
+        torch.cuda.synchronize()
+        ret.put((rank, eng.theta.cpu().numpy(), eng.fitness_all.cpu().numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('N,precision,use_graph', [(1000, 'f16x3', False), (1001, 'fp32', False), (4096, 'f16', True)])
+def test_two_gpu_generation_matches_one_gpu(N, precision, use_graph):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    sys.path.insert(0, REPO)
+    from distributedes_b200.engine import NESEngine
+    from oracle import nes_oracle as orc
+    ctx = mp.get_context('spawn')
+    ret = ctx.SimpleQueue()
+    mp.spawn(_worker, args=(2, 29700 + N % 50, N, precision, use_graph, ret), nprocs=2, join=True)
+    res = sorted([ret.get() for _ in range(2)], key=lambda r: r[0])
+    assert np.array_equal(res[0][1], res[1][1])            # identical parameters on both ranks, no broadcast
+    assert np.array_equal(res[0][2], res[1][2])
+    d0, H, A, T = 24, 64, 4, 256
+    obs, target = orc.synthetic_tape(T, d0, A)
+    one = NESEngine(state_dim=d0, hidden=H, action_dim=A, pop_size=N, theta0=orc.synthetic_theta(d0, H, A), obs=obs,
+                    target=target, sigma=0.1, learning_rate=0.1, clip=1.0, seed=21, precision=precision, device='cuda:0')
+    for _ in range(3):
+        one.generation()
+    # per-member fitness does not depend on the sharding: bit-identical
+    assert np.array_equal(one.fitness_all.cpu().numpy(), res[0][2])
+    # the update differs only by the order of the cross-shard fp32 sum
+    th1 = one.theta.cpu().numpy()
+    assert np.linalg.norm(th1 - res[0][1]) <= 1e-5 * np.linalg.norm(th1 - orc.synthetic_theta(d0, H, A))

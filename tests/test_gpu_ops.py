@@ -131,6 +131,25 @@ def test_eval_tensor_core_many_members_equals_fp32_path():
     assert torch.equal(b, ops().nes_eval(th, o, t, precision='f16x3', **kw))
 
 
+@pytest.mark.parametrize('H,T,precision', [(256, 256, 'f16x3'), (256, 512, 'f16'), (64, 384, 'f16x3')])
+def test_eval_multi_pass_tile_cache_is_transparent(H, T, precision):
+    """Shapes that need several passes over a member: with the optional workspace the weight tiles of pass 0 are
+    cached and copied back; without it they are regenerated.  Both must give bit-identical fitness."""
+    d0, A, n = 24, 4, 300
+    obs, target = orc.synthetic_tape(T, d0, A)
+    th = torch.from_numpy(orc.synthetic_theta(d0, H, A)).to(DEV)
+    o, t = torch.from_numpy(obs).to(DEV), torch.from_numpy(target).to(DEV)
+    ws = ops().eval_workspace(d0, H, A, T, precision, DEV)
+    assert ws is not None and ws.numel() > 0
+    kw = dict(hidden=H, sigma=0.1, clip=1.0, seed=4, generation=1, member_offset=5, n_local=n, precision=precision)
+    a = ops().nes_eval(th, o, t, **kw)
+    b = ops().nes_eval(th, o, t, workspace=ws, **kw)
+    assert torch.equal(a, b)
+    ref = orc.evaluate_population(th.cpu().numpy(), obs, target, 0.1, 1.0, 4, 1, 5, 8, d0, H, A)
+    assert np.max(np.abs(b[:8].cpu().numpy() - ref) / np.abs(ref)) < (3e-5 if precision == 'f16x3' else 4e-3)
+    assert ops().eval_workspace(d0, 64, A, 256, 'f16', DEV) is None          # single-pass shape: no scratch needed
+
+
 def test_eval_state_generation_overrides_argument():
     d0, H, A, T = 24, 64, 4, 64
     obs, target = orc.synthetic_tape(T, d0, A)
