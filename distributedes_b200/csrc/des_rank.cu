@@ -62,10 +62,154 @@ __global__ void rank_finish_kernel(float *__restrict__ shaped, int32_t *__restri
     shaped[i] = (float)((double)r / (double)(N - 1) - 0.5);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Large populations (N > kBucketMinN): sample-sort style bucketing makes the work ~N * (N/1024) instead of n * N.
+//   1. 4096 strided sample keys are sorted by one CTA (bitonic, shared memory) -> 1023 splitters
+//   2. every member finds its bucket by binary search over the splitters; bucket histogram (integer atomics)
+//   3. exclusive scan of the 1024 bucket counts
+//   4. members are grouped by bucket (order inside a bucket is arbitrary; it does not matter below)
+//   5. rank_i = bucket_start + #{j in bucket : (key_j, j) < (key_i, i)}     — exact, ties by index
+// Degenerate inputs (all keys equal) put everything in one bucket: still exact, cost falls back to n * N.
+constexpr int kBuckets = 1024;
+constexpr int kSamples = 4096;
+constexpr int64_t kBucketMinN = 8192;
+
+__global__ void __launch_bounds__(1024) rank_splitters_kernel(uint32_t *__restrict__ splitters,
+                                                              const float *__restrict__ fitness, int64_t N) {
+    __shared__ uint32_t sk[kSamples];
+    for (int t = threadIdx.x; t < kSamples; t += 1024) {
+        const int64_t j = (int64_t)(((unsigned __int128)t * (unsigned __int128)N) / kSamples);
+        sk[t] = order_key(__ldg(fitness + j));
+    }
+    __syncthreads();
+    for (int k = 2; k <= kSamples; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < kSamples; t += 1024) {
+                const int p = t ^ j;
+                if (p > t) {
+                    const uint32_t a = sk[t], b = sk[p];
+                    const bool up = (t & k) == 0;
+                    if ((a > b) == up) { sk[t] = b; sk[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = threadIdx.x; t < kBuckets - 1; t += 1024) splitters[t] = sk[(t + 1) * (kSamples / kBuckets)];
+}
+
+// bucket(key) = #{splitters <= key}  (monotone in key, so bucket order == key order)
+__device__ __forceinline__ int bucket_of_key(const uint32_t *sp, uint32_t key) {
+    int lo = 0, hi = kBuckets - 1;            // answer in [0, kBuckets-1]
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sp[mid] <= key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) rank_bucket_hist_kernel(int32_t *__restrict__ bucket_count,
+                                                               uint16_t *__restrict__ bucket_id, uint32_t *__restrict__ keys,
+                                                               const uint32_t *__restrict__ splitters,
+                                                               const float *__restrict__ fitness, int64_t N) {
+    __shared__ uint32_t sp[kBuckets];
+    for (int t = threadIdx.x; t < kBuckets - 1; t += 256) sp[t] = splitters[t];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    const uint32_t key = order_key(__ldg(fitness + i));
+    const int b = bucket_of_key(sp, key);
+    keys[i] = key;
+    bucket_id[i] = (uint16_t)b;
+    atomicAdd(bucket_count + b, 1);
+}
+
+__global__ void __launch_bounds__(kBuckets) rank_bucket_scan_kernel(int32_t *__restrict__ bucket_start,
+                                                                    int32_t *__restrict__ bucket_fill,
+                                                                    const int32_t *__restrict__ bucket_count) {
+    __shared__ int32_t s[kBuckets];
+    const int t = threadIdx.x;
+    s[t] = bucket_count[t];
+    __syncthreads();
+    for (int o = 1; o < kBuckets; o <<= 1) {          // Hillis-Steele inclusive scan
+        const int32_t v = (t >= o) ? s[t - o] : 0;
+        __syncthreads();
+        s[t] += v;
+        __syncthreads();
+    }
+    bucket_start[t] = s[t] - bucket_count[t];
+    bucket_fill[t] = 0;
+}
+
+__global__ void __launch_bounds__(256) rank_bucket_group_kernel(uint32_t *__restrict__ g_key, int32_t *__restrict__ g_idx,
+                                                                int32_t *__restrict__ bucket_fill,
+                                                                const int32_t *__restrict__ bucket_start,
+                                                                const uint16_t *__restrict__ bucket_id,
+                                                                const uint32_t *__restrict__ keys, int64_t N) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    const int b = bucket_id[i];
+    const int pos = bucket_start[b] + atomicAdd(bucket_fill + b, 1);
+    g_key[pos] = keys[i];
+    g_idx[pos] = (int32_t)i;
+}
+
+__global__ void __launch_bounds__(256) rank_bucket_finish_kernel(float *__restrict__ shaped, int32_t *__restrict__ rank_out,
+                                                                 const uint32_t *__restrict__ g_key,
+                                                                 const int32_t *__restrict__ g_idx,
+                                                                 const int32_t *__restrict__ bucket_start,
+                                                                 const int32_t *__restrict__ bucket_count,
+                                                                 const uint16_t *__restrict__ bucket_id,
+                                                                 const uint32_t *__restrict__ keys, int64_t N,
+                                                                 int64_t member_offset, int64_t n_local) {
+    const int64_t il = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (il >= n_local) return;
+    const int64_t ig = member_offset + il;
+    const int b = bucket_id[ig];
+    const int start = bucket_start[b], cnt = bucket_count[b];
+    const uint64_t mine = ((uint64_t)keys[ig] << 32) | (uint64_t)(uint32_t)ig;
+    int32_t r = start;
+    for (int t = 0; t < cnt; ++t) {
+        const uint64_t other = ((uint64_t)__ldg(g_key + start + t) << 32) | (uint64_t)(uint32_t)__ldg(g_idx + start + t);
+        r += (other < mine) ? 1 : 0;
+    }
+    if (rank_out) rank_out[il] = r;
+    shaped[il] = (float)((double)r / (double)(N - 1) - 0.5);
+}
+
+struct BucketWs {        // carved out of the caller's workspace (all 16-byte aligned)
+    uint32_t *splitters, *keys, *g_key;
+    int32_t *bucket_count, *bucket_start, *bucket_fill, *g_idx;
+    uint16_t *bucket_id;
+};
+static size_t bucket_ws_bytes(int64_t N) {
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    return al(kBuckets * 4) * 4 + al((size_t)N * 4) * 3 + al((size_t)N * 2) + 256;
+}
+static BucketWs carve(void *ws, int64_t N) {
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    uint8_t *p = (uint8_t *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    BucketWs w;
+    w.splitters = (uint32_t *)p; p += al(kBuckets * 4);
+    w.bucket_count = (int32_t *)p; p += al(kBuckets * 4);
+    w.bucket_start = (int32_t *)p; p += al(kBuckets * 4);
+    w.bucket_fill = (int32_t *)p; p += al(kBuckets * 4);
+    w.keys = (uint32_t *)p; p += al((size_t)N * 4);
+    w.g_key = (uint32_t *)p; p += al((size_t)N * 4);
+    w.g_idx = (int32_t *)p; p += al((size_t)N * 4);
+    w.bucket_id = (uint16_t *)p;
+    return w;
+}
+
 }  // namespace des
 
+// The workspace depends on N only through the bucketed path; callers size it with des_rank_workspace_bytes_n.
 extern "C" DES_API size_t des_rank_workspace_bytes(int64_t n_local) {
     return n_local > 0 ? (size_t)n_local * sizeof(int32_t) : 0;
+}
+extern "C" DES_API size_t des_rank_workspace_bytes_n(int64_t N, int64_t n_local) {
+    const size_t base = des_rank_workspace_bytes(n_local);
+    return N > des::kBucketMinN ? (base > des::bucket_ws_bytes(N) ? base : des::bucket_ws_bytes(N)) : base;
 }
 
 extern "C" DES_API int des_centered_rank(float *shaped_out_dev, int32_t *rank_out_dev, const float *fitness_all_dev, int64_t N,
@@ -85,6 +229,20 @@ extern "C" DES_API int des_centered_rank(float *shaped_out_dev, int32_t *rank_ou
         return DES_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (N > kBucketMinN && workspace_bytes >= bucket_ws_bytes(N)) {
+        const BucketWs w = carve(workspace_dev, N);
+        const unsigned gn = (unsigned)((N + 255) / 256);
+        DES_CUDA(cudaMemsetAsync(w.bucket_count, 0, kBuckets * sizeof(int32_t), st));
+        rank_splitters_kernel<<<1, 1024, 0, st>>>(w.splitters, fitness_all_dev, N);
+        rank_bucket_hist_kernel<<<gn, 256, 0, st>>>(w.bucket_count, w.bucket_id, w.keys, w.splitters, fitness_all_dev, N);
+        rank_bucket_scan_kernel<<<1, kBuckets, 0, st>>>(w.bucket_start, w.bucket_fill, w.bucket_count);
+        rank_bucket_group_kernel<<<gn, 256, 0, st>>>(w.g_key, w.g_idx, w.bucket_fill, w.bucket_start, w.bucket_id, w.keys, N);
+        rank_bucket_finish_kernel<<<(unsigned)((n_local + 255) / 256), 256, 0, st>>>(
+            shaped_out_dev, rank_out_dev, w.g_key, w.g_idx, w.bucket_start, w.bucket_count, w.bucket_id, w.keys, N,
+            member_offset, n_local);
+        DES_LAUNCH_CHECK("rank_bucket kernels");
+        return DES_OK;
+    }
     int32_t *counts = (int32_t *)workspace_dev;
     DES_CUDA(cudaMemsetAsync(counts, 0, (size_t)n_local * sizeof(int32_t), st));
     const unsigned bx = (unsigned)((n_local + kRankThreads - 1) / kRankThreads);

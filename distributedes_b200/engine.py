@@ -67,15 +67,18 @@ class NESEngine:
         self.partial = torch.zeros(self.P, dtype=torch.float32, device=dev)
         self.update = torch.zeros(self.P, dtype=torch.float32, device=dev)
         self.state = self.k.new_state(dev, 0)
-        self.rank_ws = self.k.rank_workspace(self.n_local, dev)
+        self.rank_ws = self.k.rank_workspace(self.n_local, dev, self.N)
         self.grad_ws = self.k.grad_workspace(self.n_local, self.P, dev)
         self.set_tape(obs, target)
         self.eval_ws = (self.k.eval_workspace(self.d0, self.H, self.A, self.T, precision, dev)
                         if hasattr(self.k, 'eval_workspace') else None)
         self.generation_index = 0
         self._graph = None
-        # NCCL collectives are capturable (torch >= 2.x, NCCL >= 2.9): the graph then holds kernels AND collectives
-        self._use_graph = bool(use_graph) and self.device.type == 'cuda'
+        # single GPU: the whole generation is one CUDA graph.  With a process group the generation stays eager
+        # unless DES_GRAPH_NCCL=1 (capturing ProcessGroupNCCL collectives is opt-in: it hung on the 2-GPU box).
+        import os
+        self._use_graph = (bool(use_graph) and self.device.type == 'cuda'
+                           and (self.world == 1 or os.environ.get('DES_GRAPH_NCCL') == '1'))
 
     # -- inputs ------------------------------------------------------------------------------------------
     def set_tape(self, obs, target):

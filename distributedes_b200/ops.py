@@ -127,8 +127,9 @@ def nes_eval(theta, obs, target, *, hidden, sigma, clip, seed, generation=0, sta
     return out
 
 
-def rank_workspace(n_local, device):
-    nbytes = _lib.load().des_rank_workspace_bytes(n_local)
+def rank_workspace(n_local, device, N=None):
+    lib = _lib.load()
+    nbytes = lib.des_rank_workspace_bytes_n(N, n_local) if N is not None else lib.des_rank_workspace_bytes(n_local)
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
@@ -143,7 +144,7 @@ def centered_rank(fitness_all, member_offset=0, n_local=None, *, workspace=None,
         out = torch.empty(n_local, dtype=torch.float32, device=dev)
     ranks = torch.empty(n_local, dtype=torch.int32, device=dev) if return_ranks else None
     if workspace is None:
-        workspace = rank_workspace(n_local, dev)
+        workspace = rank_workspace(n_local, dev, N)
     with _on(fitness_all, 'fitness_all'):
         _lib.check(_lib.load().des_centered_rank(
             _ptr(out, torch.float32, 'out'), _ptr(ranks, torch.int32, 'ranks', allow_none=True),

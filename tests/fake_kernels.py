@@ -22,7 +22,7 @@ def state_advance(state, beta1=0.9, beta2=0.999):
     state[3] *= beta2
 
 
-def rank_workspace(n_local, device):
+def rank_workspace(n_local, device, N=None):
     return torch.empty(0)
 
 

@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, N, gens, ret):
+def _worker(rank, world, port, N, gens, outdir):
     sys.path.insert(0, REPO)
     sys.path.insert(0, os.path.join(REPO, 'tests'))
     import fake_kernels
@@ -31,7 +31,8 @@ def _worker(rank, world, port, N, gens, ret):
         for _ in range(gens):
             eng.generation()
             fits.append(eng.fitness_all.numpy().copy())
-        ret.put((rank, eng.offset, eng.n_local, eng.theta.numpy().copy(), np.stack(fits)))
+        np.savez(os.path.join(outdir, 'rank%d.npz' % rank), offset=eng.offset, n_local=eng.n_local,
+                 theta=eng.theta.numpy(), fits=np.stack(fits))
     finally:
         dist.destroy_process_group()
 
@@ -39,12 +40,15 @@ def _worker(rank, world, port, N, gens, ret):
 @pytest.mark.parametrize('N,world', [(10, 2), (11, 2), (3, 2)])
 def test_sharded_generation_equals_single_process(N, world):
     from oracle import nes_oracle as orc
-    ctx = mp.get_context('spawn')
-    ret = ctx.SimpleQueue()
+    import tempfile
     port = 29600 + N
     gens = 2
-    mp.spawn(_worker, args=(world, port, N, gens, ret), nprocs=world, join=True)
-    results = sorted([ret.get() for _ in range(world)], key=lambda r: r[0])
+    with tempfile.TemporaryDirectory() as outdir:
+        mp.spawn(_worker, args=(world, port, N, gens, outdir), nprocs=world, join=True)
+        results = []
+        for r in range(world):
+            z = np.load(os.path.join(outdir, 'rank%d.npz' % r))
+            results.append((r, int(z['offset']), int(z['n_local']), z['theta'], z['fits']))
     # shards tile the population
     assert results[0][1] == 0 and sum(r[2] for r in results) == N
     # every rank ends with bit-identical parameters (no broadcast needed)

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, N, precision, use_graph, ret):
+def _worker(rank, world, port, N, precision, use_graph, outdir, gens):
     sys.path.insert(0, REPO)
     from distributedes_b200.engine import NESEngine
     from oracle import nes_oracle as orc
@@ -27,10 +27,15 @@ def _worker(rank, world, port, N, precision, use_graph, ret):
         eng = NESEngine(state_dim=d0, hidden=H, action_dim=A, pop_size=N, theta0=orc.synthetic_theta(d0, H, A), obs=obs,
                         target=target, sigma=0.1, learning_rate=0.1, clip=1.0, seed=21, precision=precision,
                         device='cuda:%d' % rank, use_graph=use_graph)
-        for _ in range(3):
+        fit0 = theta1 = None
+        for g in range(gens):
             eng.generation()
+            if g == 0:
+                fit0 = eng.fitness_all.cpu().numpy()
+                theta1 = eng.theta.cpu().numpy()
         torch.cuda.synchronize()
-        ret.put((rank, eng.theta.cpu().numpy(), eng.fitness_all.cpu().numpy()))
+        # results go through files: a SimpleQueue pipe (64 KB) would block the child while the parent joins
+        np.savez(os.path.join(outdir, 'rank%d.npz' % rank), theta=eng.theta.cpu().numpy(), fitness=fit0, theta1=theta1)
     finally:
         dist.destroy_process_group()
 
@@ -42,20 +47,24 @@ def test_two_gpu_generation_matches_one_gpu(N, precision, use_graph):
     sys.path.insert(0, REPO)
     from distributedes_b200.engine import NESEngine
     from oracle import nes_oracle as orc
-    ctx = mp.get_context('spawn')
-    ret = ctx.SimpleQueue()
-    mp.spawn(_worker, args=(2, 29700 + N % 50, N, precision, use_graph, ret), nprocs=2, join=True)
-    res = sorted([ret.get() for _ in range(2)], key=lambda r: r[0])
+    import tempfile
+    with tempfile.TemporaryDirectory() as outdir:
+        mp.spawn(_worker, args=(2, 29700 + N % 50, N, precision, use_graph, outdir, 3), nprocs=2, join=True)
+        res = []
+        for r in range(2):
+            z = np.load(os.path.join(outdir, 'rank%d.npz' % r))
+            res.append((r, z['theta'], z['fitness'], z['theta1']))
     assert np.array_equal(res[0][1], res[1][1])            # identical parameters on both ranks, no broadcast
     assert np.array_equal(res[0][2], res[1][2])
     d0, H, A, T = 24, 64, 4, 256
     obs, target = orc.synthetic_tape(T, d0, A)
     one = NESEngine(state_dim=d0, hidden=H, action_dim=A, pop_size=N, theta0=orc.synthetic_theta(d0, H, A), obs=obs,
                     target=target, sigma=0.1, learning_rate=0.1, clip=1.0, seed=21, precision=precision, device='cuda:0')
-    for _ in range(3):
-        one.generation()
-    # per-member fitness does not depend on the sharding: bit-identical
+    one.generation()
+    # generation-0 fitness of a member does not depend on the sharding: bit-identical
     assert np.array_equal(one.fitness_all.cpu().numpy(), res[0][2])
-    # the update differs only by the order of the cross-shard fp32 sum
+    # the first update differs only by the order of the cross-shard fp32 sum.  (Later generations are not compared:
+    # parameters that differ in the last bit flip near-tied ranks, which moves the update by ~5/N^1.5 per flip.)
+    th0 = orc.synthetic_theta(d0, H, A)
     th1 = one.theta.cpu().numpy()
-    assert np.linalg.norm(th1 - res[0][1]) <= 1e-5 * np.linalg.norm(th1 - orc.synthetic_theta(d0, H, A))
+    assert np.linalg.norm(th1 - res[0][3]) <= 1e-5 * np.linalg.norm(th1 - th0)
