@@ -290,7 +290,8 @@ def run_ours(a):
             cpu = {'value': None, 'unit': 'policy-evals/s', 'cores': None, 'kind': 'port', 'sample': 'failed: %s' % e}
 
     if rank == 0:
-        launches_per_step = 7          # eval, rank_count, rank_finish, grad_chunk, grad_reduce, apply, state_advance
+        # eval, rank (2 kernels; 5 on the bucketed path for N > 8192), grad_chunk, grad_reduce, apply, state_advance
+        launches_per_step = 5 + (5 if N > 8192 else 2)
         line = {
             'metric': 'nes_policy_evals_per_sec', 'value': value, 'unit': 'policy-evals/s', 'n_gpus': world,
             'steps': a.steps, 'warmup': max(a.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
