@@ -40,6 +40,8 @@ SIGNATURES = {
     'des_param_count': (_I64, [_I32, _I32, _I32]),
     'des_noise_fill': (C.c_int, [_P, _I64, _I64, _U64, _U64, _I64, _U32, _P]),
     'des_nes_perturb': (C.c_int, [_P, _P, _I64, _I64, _D, _U64, _U64, _I64, _P]),
+    'des_obs_stats_merge': (C.c_int, [_P, _P, _I32, _I32, _D, _P]),
+    'des_obs_normalize': (C.c_int, [_P, _P, _P, _I32, _I32, _P]),
     'des_nes_eval_workspace_bytes': (_SZ, [Dims, C.c_int]),
     'des_nes_eval': (C.c_int, [_P, _P, _P, _P, Dims, _D, _D, _U64, _U64, _P, _I64, _I64, C.c_int, _P, _SZ, _P]),
     'des_rank_workspace_bytes': (_SZ, [_I64]),

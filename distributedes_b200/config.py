@@ -36,6 +36,7 @@ class BasicConfig:
         self.seed = 0
         self.precision = 'fp32'
         self.max_generations = 0      # 0 = unbounded (stop on max_steps like the reference)
+        self.normalize_obs = False    # True = the reference's StaticNormalizer/SharedStats behaviour (utils.py:37-106)
 
 
 class SynthTapeConfig(BasicConfig):

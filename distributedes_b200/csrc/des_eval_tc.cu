@@ -77,6 +77,7 @@ struct TcBars {
     uint64_t h_ready[2], h_free[2];
     uint32_t tmem_base;
     float fit_part[16];
+    float act_x[128][kMaxA];     // NT == 1: action partial sums handed from the half-1 warp to the half-0 warp
 };
 
 // eps for 8 consecutive flat parameters starting at j0 (multiple of 4): two quads.
@@ -147,10 +148,12 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
 }
 
 template <int H, int MODE, int NT>
-__global__ void __launch_bounds__((4 * NT + kGenWarps + 1) * 32, 1) eval_tc_kernel(TcArgs a) {
+__global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(TcArgs a) {
     using C = TcCfg<H, MODE>;
     constexpr bool X3 = C::X3;
-    constexpr int kEpiWarps = 4 * NT;
+    constexpr int kEpiWarps = 8;              // NT == 2: four per tile slot; NT == 1: two per TMEM lane quadrant,
+                                              // each taking one 32-column half of every accumulator chunk
+    constexpr int kWarpsPerSlot = kEpiWarps / NT;
     constexpr int kMmaWarp = kEpiWarps + kGenWarps;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -174,11 +177,11 @@ __global__ void __launch_bounds__((4 * NT + kGenWarps + 1) * 32, 1) eval_tc_kern
             for (int p = 0; p < 2; ++p) {
                 mbar_init(smem_u32(&bars->small_full[p]), kGenWarps);
                 mbar_init(smem_u32(&bars->small_empty[p]), n_epi_warps);
-                mbar_init(smem_u32(&bars->h_ready[p]), 4);
+                mbar_init(smem_u32(&bars->h_ready[p]), kWarpsPerSlot);
                 mbar_init(smem_u32(&bars->h_free[p]), 1);
                 for (int st = 0; st < 2; ++st) {
                     mbar_init(smem_u32(&bars->acc_full[p][st]), 1);
-                    mbar_init(smem_u32(&bars->acc_empty[p][st]), 4);
+                    mbar_init(smem_u32(&bars->acc_empty[p][st]), kWarpsPerSlot);
                 }
             }
             fence_barrier_init();
@@ -296,8 +299,9 @@ __global__ void __launch_bounds__((4 * NT + kGenWarps + 1) * 32, 1) eval_tc_kern
         }
     } else if (warp < kEpiWarps) {
         // =================================== epilogue warps ============================================
-        if (NT == 2) reg_alloc<96>();
-        const int ts = warp >> 2;                                     // tile slot
+        reg_alloc<96>();
+        const int ts = (NT == 2) ? (warp >> 2) : 0;                   // tile slot
+        const int my_half = warp >> 2;                                // NT == 1: the 32-column half this warp owns
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
         const int row = (warp & 3) * 32 + lane;                       // observation row inside the tile
         uint32_t acc_u = 0, hv = 0, mi = 0;
@@ -316,15 +320,16 @@ __global__ void __launch_bounds__((4 * NT + kGenWarps + 1) * 32, 1) eval_tc_kern
                     tc_fence_after();
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
+                        if (NT == 1 && half != my_half) continue;
                         uint32_t v[32];
                         tmem_ld32(sbase + C::ACOLS + st * kNC + half * 32, v);
                         tmem_wait_ld();
-                        if (half == 1) {
+                        if (half == 1 || NT == 1) {
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ts][st]));
                         }
-                        if (nc == 0 && half == 0) {
+                        if (nc == 0 && (half == 0 || NT == 1)) {
                             // the previous (member, pass) must have finished reading H1 before we overwrite it
                             mbar_wait(smem_u32(&bars->h_free[ts]), (hv & 1) ^ 1);
                             tc_fence_after();
@@ -372,10 +377,11 @@ __global__ void __launch_bounds__((4 * NT + kGenWarps + 1) * 32, 1) eval_tc_kern
                     tc_fence_after();
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
+                        if (NT == 1 && half != my_half) continue;
                         uint32_t v[32];
                         tmem_ld32(sbase + C::ACOLS + st * kNC + half * 32, v);
                         tmem_wait_ld();
-                        if (half == 1) {
+                        if (half == 1 || NT == 1) {
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ts][st]));
@@ -404,10 +410,24 @@ __global__ void __launch_bounds__((4 * NT + kGenWarps + 1) * 32, 1) eval_tc_kern
                 float act[kMaxA];
 #pragma unroll
                 for (int q = 0; q < kMaxA; ++q) act[q] = actp[q].x + actp[q].y;
+                if (NT == 1) {
+                    // the two warps of a lane quadrant each hold the action sums over their half of the features:
+                    // combine (fixed order: half 0 + half 1) before the nonlinear clip
+                    if (my_half == 1) {
+#pragma unroll
+                        for (int q = 0; q < kMaxA; ++q) bars->act_x[row][q] = act[q];
+                    }
+                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                    if (my_half == 0) {
+#pragma unroll
+                        for (int q = 0; q < kMaxA; ++q) act[q] += bars->act_x[row][q];
+                    }
+                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                }
                 const int t = (pass * NT + ts) * 128 + row;
 #pragma unroll
                 for (int q = 0; q < kMaxA; ++q) {
-                    if (q < L.A) {
+                    if (q < L.A && (NT == 2 || my_half == 0)) {
                         float v = act[q] + b3[q];
                         v = fminf(fmaxf(v, -a.clip), a.clip);
                         const float d = v - __ldg(a.target + (int64_t)t * L.A + q);
@@ -431,7 +451,7 @@ __global__ void __launch_bounds__((4 * NT + kGenWarps + 1) * 32, 1) eval_tc_kern
         }
     } else {
         // =================================== weight generators =========================================
-        if (NT == 2) reg_dealloc<56>();
+        reg_dealloc<56>();
         const int gtid = threadIdx.x - kEpiWarps * 32;                  // 0..511
         uint32_t rs = 0, rph = 0, mi = 0;     // ring cursor: slot index and phase
         constexpr int kSlotsPerMember = C::NCH + C::NCH * C::KAT;
@@ -568,7 +588,7 @@ static int launch_tc_nt(TcArgs &a, cudaStream_t st) {
     DES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     DES_CUDA(cudaFuncSetAttribute(eval_tc_kernel<H, MODE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = a.n_local < sms ? a.n_local : sms;
-    const int threads = (4 * NT + kGenWarps + 1) * 32;
+    const int threads = (8 + kGenWarps + 1) * 32;
     eval_tc_kernel<H, MODE, NT><<<(unsigned)grid, threads, smem, st>>>(a);
     DES_LAUNCH_CHECK("eval_tc_kernel");
     return DES_OK;

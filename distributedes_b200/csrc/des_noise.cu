@@ -69,3 +69,74 @@ extern "C" DES_API int des_nes_perturb(float *theta_out_dev, const float *theta_
     return des::launch_rows(true, theta_out_dev, theta_dev, n_members, P, sigma, seed, generation, member_offset,
                             des::kStreamNesEps, (cudaStream_t)stream);
 }
+
+// ---- observation normaliser: StaticNormalizer / SharedStats, utils.py:37-106 ---------------------
+// In the reference every worker feeds each observation into online Welford statistics (utils.py:68-73) and, after
+// the generation, the master Chan-merges them into the shared statistics (utils.py:85-96); observations are
+// normalised with the statistics of the PREVIOUS generations, (o - m)/sqrt(v + 1e-6), raw while n == 0
+// (utils.py:48-51).  On the tape environment every member sees the same T observations, so one generation's
+// online statistics are the tape's mean / population variance with weight n_feed = members * T.
+namespace des {
+
+// stats layout (device, fp32 like the reference's torch tensors): m[d0] | v[d0] | n[1]
+__global__ void obs_stats_merge_kernel(float *__restrict__ stats, const float *__restrict__ obs, int T, int d0,
+                                       double n_feed) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= d0) return;
+    // batch statistics of the tape column k (fp64 two-pass; the reference accumulates them one sample at a time)
+    double s = 0.0;
+    for (int t = 0; t < T; ++t) s += (double)obs[(int64_t)t * d0 + k];
+    const double mb = s / T;
+    double q = 0.0;
+    for (int t = 0; t < T; ++t) {
+        const double d = (double)obs[(int64_t)t * d0 + k] - mb;
+        q += d * d;
+    }
+    const double vb = q / T;
+    // SharedStats.merge, utils.py:85-96 (A = shared stats, B = this generation's online stats)
+    const double nA = (double)stats[2 * d0], nB = n_feed, n = nA + nB;
+    const double mA = (double)stats[k], vA = (double)stats[d0 + k];
+    const double delta = mb - mA;
+    const double m = mA + delta * nB / n;
+    const double v = (vA * nA + vb * nB + delta * delta * nA * nB / n) / n;
+    __syncthreads();                      // every thread has read n before thread 0 updates it (single block)
+    stats[k] = (float)m;
+    stats[d0 + k] = (float)v;
+    if (k == 0) stats[2 * d0] = (float)n;
+}
+
+__global__ void obs_normalize_kernel(float *__restrict__ out, const float *__restrict__ obs, const float *__restrict__ stats,
+                                     int T, int d0) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)T * d0) return;
+    const int k = (int)(i % d0);
+    const float o = obs[i];
+    if (stats[2 * d0] == 0.f) {           // utils.py:48-49: no statistics yet -> pass through
+        out[i] = o;
+        return;
+    }
+    const float std_ = sqrtf(stats[d0 + k] + 1e-6f);      // utils.py:50
+    out[i] = (o - stats[k]) / std_;                        // utils.py:51
+}
+
+}  // namespace des
+
+extern "C" DES_API int des_obs_stats_merge(float *stats_dev, const float *obs_dev, int32_t tape_len, int32_t state_dim,
+                                           double n_feed, void *stream) {
+    DES_REQUIRE(stats_dev && obs_dev, "des_obs_stats_merge: NULL pointer");
+    DES_REQUIRE(tape_len > 0 && state_dim > 0 && state_dim <= 1024 && n_feed > 0, "des_obs_stats_merge: bad sizes");
+    des::obs_stats_merge_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(stats_dev, obs_dev, tape_len, state_dim, n_feed);
+    DES_LAUNCH_CHECK("obs_stats_merge_kernel");
+    return DES_OK;
+}
+
+extern "C" DES_API int des_obs_normalize(float *obs_out_dev, const float *obs_dev, const float *stats_dev, int32_t tape_len,
+                                         int32_t state_dim, void *stream) {
+    DES_REQUIRE(obs_out_dev && obs_dev && stats_dev, "des_obs_normalize: NULL pointer");
+    DES_REQUIRE(tape_len > 0 && state_dim > 0, "des_obs_normalize: bad sizes");
+    const int64_t total = (int64_t)tape_len * state_dim;
+    des::obs_normalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(obs_out_dev, obs_dev, stats_dev,
+                                                                                           tape_len, state_dim);
+    DES_LAUNCH_CHECK("obs_normalize_kernel");
+    return DES_OK;
+}

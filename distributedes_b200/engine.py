@@ -34,7 +34,7 @@ def shard_bounds(N, world_size, rank):
 class NESEngine:
     def __init__(self, *, state_dim, hidden, action_dim, pop_size, theta0, obs, target, sigma, learning_rate,
                  weight_decay=0.005, clip=1.0, seed=0, precision='fp32', beta1=0.9, beta2=0.999, epsilon=1e-8,
-                 device=None, process_group=None, kernels=None, use_graph=False):
+                 device=None, process_group=None, kernels=None, use_graph=False, normalize_obs=False, repetitions=1):
         if kernels is None:
             from . import ops as kernels          # loads libdes_b200.so; raises if it is missing
         self.k = kernels
@@ -69,6 +69,10 @@ class NESEngine:
         self.state = self.k.new_state(dev, 0)
         self.rank_ws = self.k.rank_workspace(self.n_local, dev, self.N)
         self.grad_ws = self.k.grad_workspace(self.n_local, self.P, dev)
+        # observation normaliser (StaticNormalizer / SharedStats, utils.py:37-106): device-resident [m | v | n]
+        self.normalize_obs = bool(normalize_obs)
+        self.repetitions = int(repetitions)
+        self.obs_stats = torch.zeros(2 * self.d0 + 1, dtype=torch.float32, device=dev) if self.normalize_obs else None
         self.set_tape(obs, target)
         self.eval_ws = (self.k.eval_workspace(self.d0, self.H, self.A, self.T, precision, dev)
                         if hasattr(self.k, 'eval_workspace') else None)
@@ -88,17 +92,21 @@ class NESEngine:
                 or target.shape[0] != obs.shape[0]:
             raise ValueError('tape shapes %r / %r do not match (T,%d) / (T,%d)' %
                              (tuple(obs.shape), tuple(target.shape), self.d0, self.A))
-        if getattr(self, 'obs', None) is not None and self.obs.shape == obs.shape:
-            self.obs.copy_(obs, non_blocking=True)          # keep addresses stable for a captured graph
+        if getattr(self, 'obs_raw', None) is not None and self.obs_raw.shape == obs.shape:
+            self.obs_raw.copy_(obs, non_blocking=True)      # keep addresses stable for a captured graph
             self.target.copy_(target, non_blocking=True)
         else:
-            self.obs = obs.to(self.device).contiguous()
+            self.obs_raw = obs.to(self.device).contiguous()
             self.target = target.to(self.device).contiguous()
+            # what the kernels read: the raw tape, or its normalised image refreshed every generation
+            self.obs = torch.empty_like(self.obs_raw) if self.normalize_obs else self.obs_raw
             self._graph = None
         self.T = int(obs.shape[0])
 
     # -- the three phases around the two collectives -------------------------------------------------------
     def evaluate(self):
+        if self.normalize_obs:        # utils.py:48-51 with the statistics of the previous generations
+            self.k.obs_normalize(self.obs_raw, self.obs_stats, out=self.obs)
         if self.world > 1:
             self.fitness_all.zero_()
         if self.n_local:
@@ -123,6 +131,10 @@ class NESEngine:
                          learning_rate=self.lr, weight_decay=self.wd, beta1=self.beta1, beta2=self.beta2,
                          epsilon=self.epsilon, update_out=self.update)
         self.k.state_advance(self.state, self.beta1, self.beta2)
+        if self.normalize_obs:
+            # natural_es.py:85-89: merge this generation's online statistics (every member saw the whole tape;
+            # all ranks hold identical online stats, so the merged result needs no collective)
+            self.k.obs_stats_merge(self.obs_stats, self.obs_raw, self.N * self.T * self.repetitions)
 
     def _generation_eager(self):
         self.evaluate()
@@ -142,7 +154,8 @@ class NESEngine:
     def _capture(self):
         """Capture eval -> rank -> grad -> apply -> advance as one CUDA graph.  Generation / Adam counters
         live in device memory (des_state), so the same graph is replayed every generation."""
-        saved = [t.clone() for t in (self.theta, self.adam_m, self.adam_v, self.state)]
+        live = [self.theta, self.adam_m, self.adam_v, self.state] + ([self.obs_stats] if self.normalize_obs else [])
+        saved = [t.clone() for t in live]
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
@@ -151,7 +164,7 @@ class NESEngine:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._generation_eager()
-        for t, v in zip((self.theta, self.adam_m, self.adam_v, self.state), saved):
+        for t, v in zip(live, saved):
             t.copy_(v)                                # capture does not execute, the warm-up did: roll it back
         self._graph = g
 
@@ -173,9 +186,20 @@ class NESEngine:
         """Return of the tape episode for one flat solution (test(), natural_es.py:101-110)."""
         theta = self.theta if solution is None else torch.as_tensor(
             np.ascontiguousarray(solution, dtype=np.float32)).to(self.device)
-        out = self.k.nes_eval(theta, self.obs, self.target, hidden=self.H, sigma=0.0, clip=self.clip, seed=self.seed,
+        obs = self.obs_raw
+        if self.normalize_obs:
+            obs = self.k.obs_normalize(self.obs_raw, self.obs_stats)
+        out = self.k.nes_eval(theta, obs, self.target, hidden=self.H, sigma=0.0, clip=self.clip, seed=self.seed,
                               generation=0, member_offset=0, n_local=1, precision='fp32')
         return float(out[0])
+
+    def stats_state_dict(self):
+        """SharedStats.state_dict (utils.py:98-101) of the device-resident statistics."""
+        if not self.normalize_obs:
+            z = np.zeros(self.d0, dtype=np.float32)
+            return {'m': z, 'v': z.copy(), 'n': np.zeros(1, dtype=np.float32)}
+        st = self.obs_stats.cpu().numpy()
+        return {'m': st[:self.d0].copy(), 'v': st[self.d0:2 * self.d0].copy(), 'n': st[2 * self.d0:].copy()}
 
     def theta_numpy(self):
         return self.theta.detach().cpu().numpy()

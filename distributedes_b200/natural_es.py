@@ -44,7 +44,8 @@ def build_engine(config, param=None, **kw):
                      pop_size=config.pop_size, theta0=theta0, obs=env.obs, target=env.target, sigma=config.sigma,
                      learning_rate=config.learning_rate, weight_decay=config.weight_decay, clip=config.clip,
                      seed=getattr(config, 'seed', 0), precision=getattr(config, 'precision', 'fp32'),
-                     beta1=config.opt.beta1, beta2=config.opt.beta2, epsilon=config.opt.epsilon, **kw)
+                     beta1=config.opt.beta1, beta2=config.opt.beta2, epsilon=config.opt.epsilon,
+                     normalize_obs=getattr(config, 'normalize_obs', False), repetitions=config.repetitions, **kw)
 
 
 def train(config, engine=None):

@@ -96,6 +96,26 @@ def nes_perturb(theta, n_members, sigma, seed, generation, member_offset=0):
     return out
 
 
+def obs_stats_merge(stats, obs, n_feed):
+    """SharedStats.merge of one generation's online statistics on the tape env (utils.py:85-96), in place."""
+    T, d0 = obs.shape
+    with _on(obs, 'obs'):
+        _lib.check(_lib.load().des_obs_stats_merge(_ptr(stats, torch.float32, 'stats'), _ptr(obs, torch.float32, 'obs'),
+                                                   T, d0, float(n_feed), _stream()), 'des_obs_stats_merge')
+    return stats
+
+
+def obs_normalize(obs, stats, out=None):
+    """StaticNormalizer.__call__ (utils.py:42-57) over the whole tape: identity while stats are empty."""
+    T, d0 = obs.shape
+    if out is None:
+        out = torch.empty_like(obs)
+    with _on(obs, 'obs'):
+        _lib.check(_lib.load().des_obs_normalize(_ptr(out, torch.float32, 'out'), _ptr(obs, torch.float32, 'obs'),
+                                                 _ptr(stats, torch.float32, 'stats'), T, d0, _stream()), 'des_obs_normalize')
+    return out
+
+
 def eval_workspace(state_dim, hidden, action_dim, tape_len, precision, device):
     """Optional scratch for des_nes_eval (multi-pass tensor-core shapes); None when the shape needs none."""
     with torch.cuda.device(device):

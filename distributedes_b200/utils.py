@@ -1,6 +1,7 @@
 """Host-side mirror of the reference's utils.py surface for the hot path: fitness_shift (utils.py:142-148),
-Adam (utils.py:150-166), Evaluator (utils.py:108-139), StaticNormalizer/SharedStats (utils.py:37-106,
-identity-only here — the device normaliser is a SURVEY §8f 'next' row).  All arithmetic runs in
+Adam (utils.py:150-166), Evaluator (utils.py:108-139), StaticNormalizer/SharedStats (utils.py:37-106: these host
+classes only carry the empty/identity state; the live statistics are device-resident in engine.NESEngine with
+normalize_obs=True, kernels des_obs_stats_merge / des_obs_normalize).  All arithmetic runs in
 libdes_b200.so on the GPU; these classes only adapt argument/return conventions.
 """
 from __future__ import annotations
@@ -81,7 +82,8 @@ class SharedStats:
 
     def merge(self, B):
         if B.n[0] != 0:
-            raise NotImplementedError('observation statistics are not gathered on the device yet (SURVEY §8f row 1)')
+            raise NotImplementedError('host-side merging is not supported: use NESEngine(normalize_obs=True), which keeps '
+                                      'SharedStats on the device (des_obs_stats_merge)')
 
     def state_dict(self):
         return {'m': self.m, 'v': self.v, 'n': self.n}
@@ -99,7 +101,7 @@ class StaticNormalizer:
 
     def __call__(self, o_):
         if self.offline_stats.n[0] != 0:
-            raise NotImplementedError('non-empty observation statistics (SURVEY §8f row 1)')
+            raise NotImplementedError('non-empty statistics live on the device: NESEngine(normalize_obs=True)')
         return o_
 
 

@@ -106,6 +106,18 @@ DES_API int des_nes_perturb(float *theta_out_dev, const float *theta_dev, int64_
                     double sigma, uint64_t seed, uint64_t generation, int64_t member_offset,
                     void *stream);
 
+/* ---- observation normaliser (StaticNormalizer / SharedStats, utils.py:37-106) -------------------------- */
+
+/* stats_dev: fp32 [m (d0) | v (d0) | n (1)], zero-initialised = "no statistics" (utils.py:61-63).
+ * des_obs_stats_merge: Chan-merge (utils.py:85-96) the statistics of the tape obs_dev[T][d0], fed n_feed times
+ * (n_feed = members * T * repetitions: what the workers' online stats hold after one generation on the tape env),
+ * into stats_dev.  des_obs_normalize: obs_out = (obs - m)/sqrt(v + 1e-6), or obs unchanged while n == 0
+ * (utils.py:48-51).  obs_out_dev may alias obs_dev. */
+DES_API int des_obs_stats_merge(float *stats_dev, const float *obs_dev, int32_t tape_len, int32_t state_dim,
+                        double n_feed, void *stream);
+DES_API int des_obs_normalize(float *obs_out_dev, const float *obs_dev, const float *stats_dev, int32_t tape_len,
+                      int32_t state_dim, void *stream);
+
 /* ---- fused sample + forward + fitness ------------------------------------------------------ */
 
 /* fitness_out_dev[i] (i < n_local) = sum_t -|| clip(pi_{theta+sigma*eps_m}(obs_t), -clip, clip) - target_t ||^2

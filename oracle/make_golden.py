@@ -14,9 +14,10 @@ What comes from where:
                                             stub gym tape env (oracle/gym_stub)
   * one..three full generations          -> /root/reference/natural_es.py:34-99 train() run VERBATIM
                                             (1 worker; np.random.randn replaced by the Philox noise so
-                                            member identity is reproducible; SharedStats.merge disabled
-                                            = observation normaliser off; config.opt replaced
-                                            by a recording subclass of the reference Adam)
+                                            member identity is reproducible; config.opt replaced by a
+                                            recording subclass of the reference Adam; once with
+                                            SharedStats.merge disabled = observation normaliser off,
+                                            SURVEY §8d, and once with the normaliser left on)
 The only non-reference ingredient is the noise stream (oracle.nes_oracle.noise): the reference has
 no reproducible RNG (natural_es.py:23 seeds from OS entropy).
 """
@@ -137,7 +138,7 @@ def golden_eval(tag, d0, H, A, T, clip, N, seed, sigma):
              seed=seed, sigma=sigma, theta=theta, fitness=fit, steps=steps)
 
 
-def golden_train_verbatim(tag, d0, H, A, T, clip, N, seed, sigma, lr, gens):
+def golden_train_verbatim(tag, d0, H, A, T, clip, N, seed, sigma, lr, gens, normalizer=False):
     """natural_es.train() verbatim for `gens` generations (see module docstring for the three hooks)."""
     cfg = TapeConfig(d0, A, T, H, clip)
     cfg.repetitions = 1
@@ -166,7 +167,8 @@ def golden_train_verbatim(tag, d0, H, A, T, clip, N, seed, sigma, lr, gens):
 
     real_merge = ref_utils.SharedStats.merge
     np.random.randn = philox_randn
-    ref_utils.SharedStats.merge = lambda self, B: None    # observation normaliser off
+    if not normalizer:
+        ref_utils.SharedStats.merge = lambda self, B: None    # observation normaliser off
     try:
         rewards, steps, _ = ref_nes.train(cfg)
     finally:
@@ -182,7 +184,7 @@ def golden_train_verbatim(tag, d0, H, A, T, clip, N, seed, sigma, lr, gens):
         param.add_(upd)                                                   # :96
         updates.append(upd.numpy().copy())
         thetas.append(param.numpy().copy())
-    np.savez(os.path.join(OUT, 'train_%s.npz' % tag), dims=np.asarray([d0, H, A, T]), clip=clip, N=N,
+    np.savez(os.path.join(OUT, 'train_%s%s.npz' % ('norm_' if normalizer else '', tag)), dims=np.asarray([d0, H, A, T]), clip=clip, N=N,
              seed=seed, sigma=sigma, lr=lr, wd=cfg.weight_decay, gens=gens, theta0=theta0,
              grad_after_wd=np.stack(cfg.opt.rec_g), adam_step=np.stack(cfg.opt.rec_step),
              update=np.stack(updates), theta=np.stack(thetas),
@@ -197,5 +199,8 @@ if __name__ == '__main__':
     golden_eval('b64', 24, 64, 4, 16, 1.0, 24, seed=6, sigma=0.1)
     golden_train_verbatim('pend', 3, 64, 1, 32, 2.0, 16, seed=5, sigma=0.1, lr=0.1, gens=3)
     golden_train_verbatim('b64', 24, 64, 4, 16, 1.0, 24, seed=6, sigma=0.1, lr=0.1, gens=3)
+    # the same with the reference's observation normaliser left ON (SharedStats.merge untouched)
+    golden_train_verbatim('pend', 3, 64, 1, 32, 2.0, 16, seed=5, sigma=0.1, lr=0.1, gens=3, normalizer=True)
+    golden_train_verbatim('b64', 24, 64, 4, 16, 1.0, 24, seed=6, sigma=0.1, lr=0.1, gens=3, normalizer=True)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -262,6 +262,61 @@ def nes_generation(theta32, opt, obs, target, *, sigma, clip, seed, gen, N, d0, 
 
 
 # --------------------------------------------------------------------------------------------
+# Observation normaliser: SharedStats / StaticNormalizer, utils.py:37-106
+# --------------------------------------------------------------------------------------------
+class ObsStats:
+    """utils.py:59-96 restated with the reference's fp32 arithmetic (torch FloatTensors there)."""
+
+    def __init__(self, o_size):
+        self.m = np.zeros(o_size, dtype=np.float32)
+        self.v = np.zeros(o_size, dtype=np.float32)
+        self.n = np.float32(0)
+
+    def feed(self, o):
+        """utils.py:68-73 — one observation into the online (Welford) statistics."""
+        o = np.asarray(o, dtype=np.float32)
+        n = self.n
+        new_m = self.m * (n / (n + np.float32(1))) + o / (n + np.float32(1))
+        self.v = (self.v * (n / (n + np.float32(1))) + (o - self.m) * (o - new_m) / (n + np.float32(1))).astype(np.float32)
+        self.m = new_m.astype(np.float32)
+        self.n = np.float32(n + np.float32(1))
+
+    def merge(self, B):
+        """utils.py:85-96 — Chan merge of B into self."""
+        nA, nB = self.n, B.n
+        n = np.float32(nA + nB)
+        delta = B.m - self.m
+        m = self.m + delta * nB / n
+        v = self.v * nA + B.v * nB + delta * delta * nA * nB / n
+        v = v / n
+        self.m, self.v, self.n = m.astype(np.float32), v.astype(np.float32), n
+
+    def merge_tape(self, obs, n_feed):
+        """Closed form of "feed the tape n_feed/T times, then merge": the online statistics of any number of whole
+        passes over the same tape are its mean and population variance (what des_obs_stats_merge computes)."""
+        obs = np.asarray(obs, dtype=np.float64)
+        B = ObsStats(obs.shape[1])
+        B.m = obs.mean(0).astype(np.float32)
+        B.v = obs.var(0).astype(np.float32)
+        B.n = np.float32(n_feed)
+        mA, vA, nA = self.m.astype(np.float64), self.v.astype(np.float64), float(self.n)
+        mb, vb, nB = obs.mean(0), obs.var(0), float(n_feed)
+        n = nA + nB
+        delta = mb - mA
+        self.m = (mA + delta * nB / n).astype(np.float32)
+        self.v = ((vA * nA + vb * nB + delta * delta * nA * nB / n) / n).astype(np.float32)
+        self.n = np.float32(n)
+
+    def normalize(self, o):
+        """StaticNormalizer.__call__ utils.py:48-51: raw while n == 0, else (o - m)/sqrt(v + 1e-6) in fp32."""
+        o = np.asarray(o, dtype=np.float32)
+        if self.n == 0:
+            return o
+        std = (self.v + np.float32(1e-6)) ** np.float32(.5)
+        return ((o - self.m) / std).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------------
 # Synthetic inputs of SURVEY.md §8d (identical on every machine)
 # --------------------------------------------------------------------------------------------
 def synthetic_tape(T, d0, A, seed=1234):

@@ -70,3 +70,28 @@ def nes_apply(theta, adam_m, adam_v, partial_sum, N, state, *, sigma, learning_r
     adam_v.copy_(torch.from_numpy(np.asarray(opt.v)))
     if update_out is not None:
         update_out.copy_(torch.from_numpy(upd))
+
+
+def _unpack(stats, d0):
+    st = orc.ObsStats(d0)
+    a = stats.numpy()
+    st.m, st.v, st.n = a[:d0].copy(), a[d0:2 * d0].copy(), np.float32(a[2 * d0])
+    return st
+
+
+def obs_normalize(obs, stats, out=None):
+    d0 = obs.shape[1]
+    st = _unpack(stats, d0)
+    res = torch.from_numpy(np.stack([st.normalize(o) for o in obs.numpy()]))
+    if out is None:
+        return res
+    out.copy_(res)
+    return out
+
+
+def obs_stats_merge(stats, obs, n_feed):
+    d0 = obs.shape[1]
+    st = _unpack(stats, d0)
+    st.merge_tape(obs.numpy(), n_feed)
+    stats.copy_(torch.from_numpy(np.concatenate([st.m, st.v, [st.n]]).astype(np.float32)))
+    return stats

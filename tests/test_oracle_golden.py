@@ -119,3 +119,46 @@ def test_generations_match_reference_train_verbatim(golden_dir, tag):
         theta = out['theta']
         rew = orc.tape_fitness(orc.forward(theta, obs, d0, H, A), target, clip)
         assert abs(rew - g['test_rewards'][gen + 1]) < 5e-6 * abs(g['test_rewards'][gen + 1])
+
+
+def _normalised_chain(g, exact_feed):
+    """natural_es.train() with the reference's observation normaliser left ON: obs of generation g are normalised
+    with the statistics merged from generations < g (utils.py:48-51, natural_es.py:85-89)."""
+    d0, H, A, T = (int(v) for v in g['dims'])
+    N, seed, sigma, lr, wd, clip = int(g['N']), int(g['seed']), float(g['sigma']), float(g['lr']), float(g['wd']), \
+        float(g['clip'])
+    obs, target = orc.synthetic_tape(T, d0, A)
+    theta, opt, stats = g['theta0'], orc.Adam(), orc.ObsStats(d0)
+    errs = []
+    for gen in range(int(g['gens'])):
+        obs_n = np.stack([stats.normalize(o) for o in obs])
+        rew = orc.tape_fitness(orc.forward(theta, obs_n, d0, H, A), target, clip)        # test(), natural_es.py:54
+        assert abs(rew - g['test_rewards'][gen]) < 5e-6 * abs(g['test_rewards'][gen]), gen
+        out = orc.nes_generation(theta, opt, obs_n, target, sigma=sigma, clip=clip, seed=seed, gen=gen, N=N, d0=d0, H=H,
+                                 A=A, weight_decay=wd, learning_rate=lr)
+        errs.append(np.linalg.norm(out['gradient'] * (1 - wd) - g['grad_after_wd'][gen]) / np.linalg.norm(g['grad_after_wd'][gen]))
+        theta = out['theta']
+        if exact_feed:                       # the single worker feeds every raw observation of every member, in order
+            online = orc.ObsStats(d0)
+            for _ in range(N):
+                for o in obs:
+                    online.feed(o)
+            stats.merge(online)
+        else:
+            stats.merge_tape(obs, N * T)
+    return errs, theta
+
+
+@pytest.mark.parametrize('tag', ['pend', 'b64'])
+def test_generations_with_reference_normaliser_on(golden_dir, tag):
+    g = load(golden_dir, 'train_norm_%s.npz' % tag)
+    errs, theta = _normalised_chain(g, exact_feed=True)
+    assert max(errs) <= 1e-6, errs          # sequential fp32 Welford replicated: only fp32-forward noise remains
+    assert np.max(np.abs(theta - g['theta'][-1])) <= 2e-6
+    # closed form used on the GPU (tape mean / variance, fp64): same result to the fp32 noise of the online update
+    errs2, theta2 = _normalised_chain(g, exact_feed=False)
+    assert max(errs2) <= 1e-4, errs2
+    # and the normaliser matters: the no-normaliser fixture differs from generation 1 on
+    g0 = load(golden_dir, 'train_%s.npz' % tag)
+    assert np.allclose(g['grad_after_wd'][0], g0['grad_after_wd'][0])
+    assert not np.allclose(g['grad_after_wd'][1], g0['grad_after_wd'][1], rtol=1e-3)
