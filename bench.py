@@ -227,7 +227,7 @@ def run_ours(a):
     tp = os.path.join(REPO, 'profiles', 'roofline_traffic.json')
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get('%s_H%d' % (a.precision, H))
+            traffic = json.load(open(tp)).get('%s_H%d_pop%d' % (a.precision, H, eng.n_local))
         except Exception:
             traffic = None
     roofline = {'kernel': 'des_nes_eval[%s]' % a.precision, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak,
