@@ -148,7 +148,8 @@ class ClockSampler:
 def run_ours(a):
     import torch
     import torch.distributed as dist
-    from oracle import nes_oracle as orc          # synthetic inputs only (same tape/theta as the CPU arm)
+    from distributedes_b200.envs import TapeEnv                 # synthetic tape, RandomState(1234)
+    from distributedes_b200.model import StandardFCNet          # nn.Linear-style init, RandomState(0)
     from distributedes_b200.engine import NESEngine
     from distributedes_b200 import _lib
 
@@ -166,8 +167,9 @@ def run_ours(a):
         print('bench.py: --gpus %d but WORLD_SIZE=%d; using WORLD_SIZE' % (a.gpus, world), file=sys.stderr)
 
     d0, H, A, T, N = a.state_dim, a.hidden, a.action_dim, a.tape_len, a.pop
-    obs, target = orc.synthetic_tape(T, d0, A)
-    theta0 = orc.synthetic_theta(d0, H, A)
+    env = TapeEnv(d0, A, T)
+    obs, target = env.obs, env.target
+    theta0 = StandardFCNet(d0, A, H, seed=0).get_weight()
     eng = NESEngine(state_dim=d0, hidden=H, action_dim=A, pop_size=N, theta0=theta0, obs=obs, target=target,
                     sigma=0.1, learning_rate=0.1, weight_decay=0.005, clip=1.0, seed=0, precision=a.precision,
                     device=dev, use_graph=not a.no_graph)

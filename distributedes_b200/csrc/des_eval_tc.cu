@@ -29,6 +29,7 @@
 //
 // Bounds per member-tile: RNG issue (~20 instr/normal), MUFU (2/normal + 1-2/tanh), tensor
 // (2*128*(d0*H + H*H) flop; x3 in F16X3).  See DESIGN.md for the budget and measured numbers.
+#include <stdlib.h>
 #include "des_common.cuh"
 #include "des_tc.cuh"
 
@@ -39,17 +40,19 @@ using namespace tc;
 constexpr int kGenWarps = 16;
 constexpr int kGenThreads = kGenWarps * 32;
 constexpr int kK1 = 32;        // layer-1 K (state_dim zero-padded): 2 k-steps of 16
-constexpr int kNC = 64;        // accumulator chunk: 64 output features = one MMA N
 constexpr int kMaxA = 8;
 
-template <int H, int MODE>
+// PAIR = two CTAs of a cluster share one member (cta_group::2): each keeps ONE 128-row tile in its TMEM and
+// generates half of every weight tile; the accumulator chunk is then 128 features wide (64 rows of B per CTA).
+template <int H, int MODE, bool PAIR = false>
 struct TcCfg {
     static constexpr bool X3 = (MODE == DES_FWD_F16X3);
-    static constexpr int NCH = H / kNC;                       // output-feature chunks per layer
+    static constexpr int NC = PAIR ? 128 : 64;                // accumulator chunk = MMA N (output features)
+    static constexpr int NCH = H / NC;                        // output-feature chunks per layer
     static constexpr int KAT = H / 64;                        // 64-wide k atoms of layer 2
     static constexpr int ACOLS = X3 ? H : H / 2;              // TMEM columns of H1 per tile slot
-    static constexpr int SLOT_COLS = ACOLS + 2 * kNC;         // + two accumulator stages
-    static constexpr int SLOT_BYTES = (X3 ? 2 : 1) * 64 * 128;   // one B tile: 64 rows x 128 B (hi [+ lo])
+    static constexpr int SLOT_COLS = ACOLS + 2 * NC;          // + two accumulator stages
+    static constexpr int SLOT_BYTES = (X3 ? 2 : 1) * 64 * 128;   // this CTA's B tile: 64 rows x 128 B (hi [+ lo])
     static constexpr int X_TILE_BYTES = (X3 ? 2 : 1) * 128 * 128;   // one X tile: 128 rows x 128 B (hi [+ lo])
     static constexpr int SMALL_FLOATS = 2 * H + kMaxA * H + kMaxA;   // b1, b2, W3' [8][H], b3[8]
     static constexpr int NT_MAX = 512 / SLOT_COLS >= 2 ? 2 : 1;     // tile slots resident in TMEM at once
@@ -147,10 +150,14 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-template <int H, int MODE, int NT>
+template <int H, int MODE, int NT, bool PAIR>
 __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(TcArgs a) {
-    using C = TcCfg<H, MODE>;
+    static_assert(!PAIR || NT == 1, "a CTA pair keeps one tile per CTA");
+    using C = TcCfg<H, MODE, PAIR>;
     constexpr bool X3 = C::X3;
+    constexpr int kNC = C::NC;
+    constexpr int kPeers = PAIR ? 2 : 1;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;          // 0 = leader (issues the MMAs)
     constexpr int kEpiWarps = 8;              // NT == 2: four per tile slot; NT == 1: two per TMEM lane quadrant,
                                               // each taking one 32-column half of every accumulator chunk
     constexpr int kWarpsPerSlot = kEpiWarps / NT;
@@ -167,30 +174,43 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
     const Layout L = a.L;
     const uint32_t gen = a.state ? (uint32_t)a.state->generation : a.gen;
 
+    // barriers the leader's MMA thread waits on collect arrivals from BOTH CTAs of a pair (remote arrive);
+    // barriers signalled by tcgen05.commit are multicast to both CTAs.
+    auto arrive_leader = [&](uint64_t *bar) {
+        if (PAIR && rank != 0) mbar_arrive_cluster(smem_u32(bar), 0);
+        else mbar_arrive(smem_u32(bar));
+    };
+    auto commit = [&](uint64_t *bar) {
+        if (PAIR) mma2_commit(smem_u32(bar));
+        else mma_commit(smem_u32(bar));
+    };
     if (warp == kMmaWarp) {
-        tmem_alloc(smem_u32(&bars->tmem_base), 512);
         if (lane == 0) {
             for (int s = 0; s < a.n_slots; ++s) {
-                mbar_init(smem_u32(&bars->slot_full[s]), kGenWarps);
+                mbar_init(smem_u32(&bars->slot_full[s]), kGenWarps * kPeers);
                 mbar_init(smem_u32(&bars->slot_empty[s]), 1);
             }
             for (int p = 0; p < 2; ++p) {
                 mbar_init(smem_u32(&bars->small_full[p]), kGenWarps);
                 mbar_init(smem_u32(&bars->small_empty[p]), n_epi_warps);
-                mbar_init(smem_u32(&bars->h_ready[p]), kWarpsPerSlot);
+                mbar_init(smem_u32(&bars->h_ready[p]), kWarpsPerSlot * kPeers);
                 mbar_init(smem_u32(&bars->h_free[p]), 1);
                 for (int st = 0; st < 2; ++st) {
                     mbar_init(smem_u32(&bars->acc_full[p][st]), 1);
-                    mbar_init(smem_u32(&bars->acc_empty[p][st]), kWarpsPerSlot);
+                    mbar_init(smem_u32(&bars->acc_empty[p][st]), kWarpsPerSlot * kPeers);
                 }
             }
             fence_barrier_init();
         }
+        __syncwarp();
+        if (PAIR) tmem_alloc2(smem_u32(&bars->tmem_base), 512);
+        else tmem_alloc(smem_u32(&bars->tmem_base), 512);
     }
     // X -> shared memory once: fp16 (hi [, lo]) K-major SWIZZLE_128B tiles of 128 observations, k < d0 (<= 32)
     for (int idx = threadIdx.x; idx < a.n_tiles * 128 * 4; idx += blockDim.x) {
         const int c8 = idx & 3, r = (idx >> 2) & 127, tt = idx >> 9;
-        const float *orow = a.obs + (int64_t)(tt * 128 + r) * L.d0;
+        const int gt = PAIR ? tt * 2 + (int)rank : tt;             // global tile of this CTA's local tile tt
+        const float *orow = a.obs + (int64_t)(gt * 128 + r) * L.d0;
         float w[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) w[e] = (c8 * 8 + e < L.d0) ? __ldg(orow + c8 * 8 + e) : 0.f;
@@ -208,18 +228,19 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();          // the peer's barriers are initialised before anyone arrives on them
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
     // TMEM map: tile slot ts at ts*SLOT_COLS: H1 [0,ACOLS), accumulator stages at ACOLS + st*64
     auto slot_base = [&](int ts) { return tmem + (uint32_t)(ts * C::SLOT_COLS); };
 
-    const int64_t first = blockIdx.x;
-    const int64_t stride = gridDim.x;
+    const int64_t first = PAIR ? blockIdx.x / 2 : blockIdx.x;
+    const int64_t stride = PAIR ? gridDim.x / 2 : gridDim.x;
 
     if (warp == kMmaWarp) {
         // =================================== MMA issuer (one thread) ===================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = idesc_f16(128, kNC);
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = idesc_f16(PAIR ? 256 : 128, kNC);
             uint32_t rs = 0, rph = 0;            // ring cursor: slot index and phase
             uint32_t acc_u[2] = {0, 0};          // accumulator-stage use counters per tile slot
             uint32_t hv[2] = {0, 0};             // (member, pass) counter per tile slot for h_ready
@@ -242,17 +263,17 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
                             for (int ks = 0; ks < kK1 / 16; ++ks) {
                                 const uint64_t ah = smem_desc_sw128(xaddr) + (uint64_t)(ks * 2);
                                 const uint64_t bh = smem_desc_sw128(bbase) + (uint64_t)(ks * 2);
-                                mma_f16_ss(d, ah, bh, idesc, ks > 0);
+                                if (PAIR) mma2_f16_ss(d, ah, bh, idesc, ks > 0); else mma_f16_ss(d, ah, bh, idesc, ks > 0);
                                 if (X3) {
                                     const uint64_t al = smem_desc_sw128(xaddr + 16384) + (uint64_t)(ks * 2);
                                     const uint64_t bl = smem_desc_sw128(bbase + 8192) + (uint64_t)(ks * 2);
-                                    mma_f16_ss(d, al, bh, idesc, 1);                      // X_lo * W_hi
-                                    mma_f16_ss(d, ah, bl, idesc, 1);                      // X_hi * W_lo
+                                    if (PAIR) { mma2_f16_ss(d, al, bh, idesc, 1); mma2_f16_ss(d, ah, bl, idesc, 1); }
+                                    else { mma_f16_ss(d, al, bh, idesc, 1); mma_f16_ss(d, ah, bl, idesc, 1); }   // X_lo W_hi, X_hi W_lo
                                 }
                             }
-                            mma_commit(smem_u32(&bars->acc_full[ts][st]));
+                            commit(&bars->acc_full[ts][st]);
                         }
-                        mma_commit(smem_u32(&bars->slot_empty[s]));
+                        commit(&bars->slot_empty[s]);
                     }
                     // ---- layer 2: D2 chunk nc = H1 W2'[64nc:64nc+64, :]^T, k in atoms of 64
                     for (int nc = 0; nc < C::NCH; ++nc) {
@@ -276,20 +297,21 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks) {
                                     const uint64_t bh = smem_desc_sw128(bbase) + (uint64_t)(ks * 2);
-                                    mma_f16_ts(d_[ts], ah + ks * 8, bh, idesc, (ka | ks) != 0);
+                                    if (PAIR) mma2_f16_ts(d_[ts], ah + ks * 8, bh, idesc, (ka | ks) != 0);
+                                    else mma_f16_ts(d_[ts], ah + ks * 8, bh, idesc, (ka | ks) != 0);
                                     if (X3) {
                                         const uint64_t bl = smem_desc_sw128(bbase + 8192) + (uint64_t)(ks * 2);
-                                        mma_f16_ts(d_[ts], ah + H / 2 + ks * 8, bh, idesc, 1);   // H1_lo * W_hi
-                                        mma_f16_ts(d_[ts], ah + ks * 8, bl, idesc, 1);           // H1_hi * W_lo
+                                        if (PAIR) { mma2_f16_ts(d_[ts], ah + H / 2 + ks * 8, bh, idesc, 1); mma2_f16_ts(d_[ts], ah + ks * 8, bl, idesc, 1); }
+                                        else { mma_f16_ts(d_[ts], ah + H / 2 + ks * 8, bh, idesc, 1); mma_f16_ts(d_[ts], ah + ks * 8, bl, idesc, 1); }   // H1_lo W_hi, H1_hi W_lo
                                     }
                                 }
                             }
-                            mma_commit(smem_u32(&bars->slot_empty[s]));
+                            commit(&bars->slot_empty[s]);
                         }
                         for (int ts = 0; ts < NT; ++ts) {
-                            mma_commit(smem_u32(&bars->acc_full[ts][st_[ts]]));
+                            commit(&bars->acc_full[ts][st_[ts]]);
                             if (nc == C::NCH - 1) {
-                                mma_commit(smem_u32(&bars->h_free[ts]));
+                                commit(&bars->h_free[ts]);
                                 ++hv[ts];
                             }
                         }
@@ -301,7 +323,9 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
         // =================================== epilogue warps ============================================
         reg_alloc<96>();
         const int ts = (NT == 2) ? (warp >> 2) : 0;                   // tile slot
-        const int my_half = warp >> 2;                                // NT == 1: the 32-column half this warp owns
+        const int my_half = warp >> 2;                                // NT == 1: this warp owns the 32-column groups g with (g & 1) == my_half
+        constexpr int kGroups = kNC / 32;                             // 32-column groups per accumulator chunk
+        const int last_g = (NT == 2) ? kGroups - 1 : kGroups - 2 + my_half;   // after loading it, the stage is free
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
         const int row = (warp & 3) * 32 + lane;                       // observation row inside the tile
         uint32_t acc_u = 0, hv = 0, mi = 0;
@@ -319,17 +343,17 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
                     mbar_wait(smem_u32(&bars->acc_full[ts][st]), ph);
                     tc_fence_after();
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        if (NT == 1 && half != my_half) continue;
+                    for (int half = 0; half < kGroups; ++half) {            // `half` = 32-column group of the chunk
+                        if (NT == 1 && (half & 1) != my_half) continue;
                         uint32_t v[32];
                         tmem_ld32(sbase + C::ACOLS + st * kNC + half * 32, v);
                         tmem_wait_ld();
-                        if (half == 1 || NT == 1) {
+                        if (half == last_g) {
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ts][st]));
+                            if (lane == 0) arrive_leader(&bars->acc_empty[ts][st]);
                         }
-                        if (nc == 0 && (half == 0 || NT == 1)) {
+                        if (nc == 0 && half == ((NT == 2) ? 0 : my_half)) {
                             // the previous (member, pass) must have finished reading H1 before we overwrite it
                             mbar_wait(smem_u32(&bars->h_free[ts]), (hv & 1) ^ 1);
                             tc_fence_after();
@@ -358,14 +382,14 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
                                 hi[2 * i + 1] = pack_h2(tanh_fast(x2), tanh_fast(x3));
                             }
                         }
-                        tmem_st16(sbase + nc * 32 + half * 16, hi);
-                        if (X3) tmem_st16(sbase + H / 2 + nc * 32 + half * 16, lo);
+                        tmem_st16(sbase + nc * (kNC / 2) + half * 16, hi);
+                        if (X3) tmem_st16(sbase + H / 2 + nc * (kNC / 2) + half * 16, lo);
                     }
                 }
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bars->h_ready[ts]));
+                if (lane == 0) arrive_leader(&bars->h_ready[ts]);
                 ++hv;
                 // ---------------- epilogue 2+3: H2 = tanh(D2 + b2); a = H2 W3^T + b3 in fp32 registers
                 float2 actp[kMaxA];                          // (even-n, odd-n) partial sums of action q
@@ -376,15 +400,15 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
                     mbar_wait(smem_u32(&bars->acc_full[ts][st]), ph);
                     tc_fence_after();
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        if (NT == 1 && half != my_half) continue;
+                    for (int half = 0; half < kGroups; ++half) {
+                        if (NT == 1 && (half & 1) != my_half) continue;
                         uint32_t v[32];
                         tmem_ld32(sbase + C::ACOLS + st * kNC + half * 32, v);
                         tmem_wait_ld();
-                        if (half == 1 || NT == 1) {
+                        if (half == last_g) {
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ts][st]));
+                            if (lane == 0) arrive_leader(&bars->acc_empty[ts][st]);
                         }
                         const int n0 = nc * kNC + half * 32;
                         const float4 *bq = reinterpret_cast<const float4 *>(b2 + n0);
@@ -424,7 +448,7 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
                     }
                     asm volatile("bar.sync 2, 256;" ::: "memory");
                 }
-                const int t = (pass * NT + ts) * 128 + row;
+                const int t = (PAIR ? pass * 2 + (int)rank : pass * NT + ts) * 128 + row;
 #pragma unroll
                 for (int q = 0; q < kMaxA; ++q) {
                     if (q < L.A && (NT == 2 || my_half == 0)) {
@@ -445,7 +469,9 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
             if (warp == 0 && lane == 0) {
                 double f = 0.0;
                 for (int w = 0; w < n_epi_warps; ++w) f += (double)bars->fit_part[w];
-                a.fitness[m] = (float)(-f);
+                // a pair adds its two halves into the (pre-zeroed) output: two commutative fp32 adds -> deterministic
+                if (PAIR) atomicAdd(a.fitness + m, (float)(-f));
+                else a.fitness[m] = (float)(-f);
             }
             asm volatile("bar.sync 1, %0;" ::"r"(n_epi_warps * 32) : "memory");
         }
@@ -459,7 +485,8 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
                                    ? a.cache + (size_t)blockIdx.x * kSlotsPerMember * C::SLOT_BYTES : nullptr;
         // theta of this thread's W2 octet is prefetched one ring slot ahead (it does not depend on the member)
         const int r2 = gtid >> 3, c82 = gtid & 7;
-        auto w2_index = [&](int nc, int ka) { return L.off_w2 + (nc * 64 + r2) * H + ka * 64 + c82 * 8; };
+        const int row_base = PAIR ? 64 * (int)rank : 0;                  // this CTA's 64 rows of every kNC-row chunk
+        auto w2_index = [&](int nc, int ka) { return L.off_w2 + (nc * kNC + row_base + r2) * H + ka * 64 + c82 * 8; };
         float4 tn0 = __ldg(reinterpret_cast<const float4 *>(a.theta + w2_index(0, 0)));
         float4 tn1 = __ldg(reinterpret_cast<const float4 *>(a.theta + w2_index(0, 0) + 4));
         for (int64_t m = first; m < a.n_local; m += stride, ++mi) {
@@ -500,7 +527,7 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
                         put_octet<X3>(slot, gtid >> 2, gtid & 3, hi, lo);
                     } else if (gtid < 256) {   // 64 rows x 4 octets = 256 items
                         const int r = gtid >> 2, c8 = gtid & 3;
-                        const int n = nc * 64 + r;
+                        const int n = nc * kNC + row_base + r;
                         float w[8];
                         if ((L.d0 & 3) == 0) {                                // row starts are quad aligned
 #pragma unroll
@@ -525,7 +552,7 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&bars->slot_full[s]));
+                    if (lane == 0) arrive_leader(&bars->slot_full[s]);
                 }
                 // ---- layer-2 tiles: rows [64nc, +64) x k [64ka, +64) of W2'
                 for (int nc = 0; nc < C::NCH; ++nc) {
@@ -556,7 +583,7 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
                         }
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&bars->slot_full[s]));
+                        if (lane == 0) arrive_leader(&bars->slot_full[s]);
                     }
                 }
             }
@@ -564,13 +591,19 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
+    if (PAIR) cluster_sync_all();          // no CTA leaves (or frees TMEM) while its peer may still signal or read it
+    if (warp == kMmaWarp) {
+        if (PAIR) tmem_dealloc2(tmem, 512);
+        else tmem_dealloc(tmem, 512);
+    }
 }
 
-template <int H, int MODE, int NT>
+template <int H, int MODE, int NT, bool PAIR>
 static int launch_tc_nt(TcArgs &a, cudaStream_t st) {
-    using C = TcCfg<H, MODE>;
-    a.n_pass = a.n_tiles / NT;
+    using C = TcCfg<H, MODE, PAIR>;
+    const int tiles_total = a.T / 128;
+    a.n_pass = tiles_total / (PAIR ? 2 : NT);
+    a.n_tiles = PAIR ? a.n_pass : tiles_total;                 // X tiles held by ONE CTA
     const size_t fixed = 2 * C::SMALL_FLOATS * sizeof(float) + sizeof(TcBars) + 1024;
     const size_t xbytes = (size_t)a.n_tiles * C::X_TILE_BYTES;
     const int per_member = C::NCH + C::NCH * C::KAT;
@@ -586,29 +619,58 @@ static int launch_tc_nt(TcArgs &a, cudaStream_t st) {
     int dev = 0, sms = 148;
     DES_CUDA(cudaGetDevice(&dev));
     DES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    DES_CUDA(cudaFuncSetAttribute(eval_tc_kernel<H, MODE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t grid = a.n_local < sms ? a.n_local : sms;
+    DES_CUDA(cudaFuncSetAttribute(eval_tc_kernel<H, MODE, NT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = (8 + kGenWarps + 1) * 32;
-    eval_tc_kernel<H, MODE, NT><<<(unsigned)grid, threads, smem, st>>>(a);
+    if (PAIR) {
+        // each pair accumulates its two halves into the output with atomicAdd: zero it first
+        DES_CUDA(cudaMemsetAsync(a.fitness, 0, (size_t)a.n_local * sizeof(float), st));
+        const int64_t pairs = a.n_local < sms / 2 ? a.n_local : sms / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * pairs));
+        cfg.blockDim = dim3(threads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        DES_CUDA(cudaLaunchKernelEx(&cfg, eval_tc_kernel<H, MODE, NT, PAIR>, a));
+    } else {
+        const int64_t grid = a.n_local < sms ? a.n_local : sms;
+        eval_tc_kernel<H, MODE, NT, PAIR><<<(unsigned)grid, threads, smem, st>>>(a);
+    }
     DES_LAUNCH_CHECK("eval_tc_kernel");
     return DES_OK;
 }
 
+// Shapes whose two tiles do not fit one CTA's tensor memory (f16x3 at H = 256) run on CTA PAIRS: each CTA of a
+// 2-cluster keeps one tile and generates half of every weight tile (DES_TC_PAIR=0 falls back to two passes).
+static bool pair_enabled() {
+    const char *e = getenv("DES_TC_PAIR");
+    return !(e && e[0] == '0');
+}
+
 template <int H, int MODE>
 static int launch_tc(TcArgs &a, cudaStream_t st) {
-    using C = TcCfg<H, MODE>;
-    a.n_tiles = a.T / 128;
-    if (C::NT_MAX >= 2 && a.n_tiles % 2 == 0) return launch_tc_nt<H, MODE, (C::NT_MAX >= 2 ? 2 : 1)>(a, st);
-    return launch_tc_nt<H, MODE, 1>(a, st);
+    using C = TcCfg<H, MODE, false>;
+    const int tiles = a.T / 128;
+    if (C::NT_MAX >= 2 && tiles % 2 == 0) return launch_tc_nt<H, MODE, (C::NT_MAX >= 2 ? 2 : 1), false>(a, st);
+    if (C::NT_MAX < 2 && tiles % 2 == 0 && pair_enabled()) return launch_tc_nt<H, MODE, 1, true>(a, st);
+    return launch_tc_nt<H, MODE, 1, false>(a, st);
 }
 
 static void tc_shape(int H, bool x3, int T, int &n_pass, size_t &slot_bytes, int &slots_per_member) {
-    const int nch = H / kNC, acols = x3 ? H : H / 2;
-    const int nt_max = 512 / (acols + 2 * kNC) >= 2 ? 2 : 1;
+    const int acols = x3 ? H : H / 2;
+    const int nt_max = 512 / (acols + 2 * 64) >= 2 ? 2 : 1;
     const int n_tiles = T / 128;
-    n_pass = (nt_max >= 2 && n_tiles % 2 == 0) ? n_tiles / 2 : n_tiles;
+    const bool two_per_pass = n_tiles % 2 == 0 && (nt_max >= 2 || pair_enabled());
+    n_pass = two_per_pass ? n_tiles / 2 : n_tiles;
+    const int nc = (nt_max < 2 && n_tiles % 2 == 0 && pair_enabled()) ? 128 : 64;
     slot_bytes = (size_t)(x3 ? 2 : 1) * 64 * 128;
-    slots_per_member = nch + nch * (H / 64);
+    slots_per_member = H / nc + (H / nc) * (H / 64);
 }
 
 size_t eval_tc_workspace_bytes(des_dims dims, int precision) {

@@ -146,3 +146,17 @@ def test_config_surface_matches_reference_attributes():
     assert np.array_equal(c.action_clip(np.asarray([-3.0, 0.5, 3.0])), [-2.0, 0.5, 2.0])   # config.py:29
     b = BipedalWalkerConfig(64)
     assert (b.state_dim, b.action_dim, len(b.initial_weight)) == (24, 4, 6020)
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under distributedes_b200/ (nor the GPU arm of bench.py) may import it."""
+    import glob
+    pkg = os.path.join(REPO, 'distributedes_b200')
+    for f in glob.glob(os.path.join(pkg, '**', '*'), recursive=True):
+        if os.path.isfile(f) and f.endswith(('.py', '.cu', '.cuh', '.h')):
+            txt = open(f).read()
+            assert not re.search(r'^\s*(from|import)\s+oracle', txt, re.M), f
+            assert not re.search(r'#\s*include\s*["<][^">]*oracle', txt), f          # comments may cite it, code may not
+    bench = open(os.path.join(REPO, 'bench.py')).read()
+    ours = bench.split('def run_ours')[1].split("if __name__ == '__main__'")[0]
+    assert not re.search(r'^\s*(from|import)\s+oracle', ours, re.M)      # only the cpu subprocess leg uses it

@@ -131,7 +131,7 @@ def test_eval_tensor_core_many_members_equals_fp32_path():
     assert torch.equal(b, ops().nes_eval(th, o, t, precision='f16x3', **kw))
 
 
-@pytest.mark.parametrize('H,T,precision', [(256, 256, 'f16x3'), (256, 512, 'f16'), (64, 384, 'f16x3')])
+@pytest.mark.parametrize('H,T,precision', [(256, 512, 'f16x3'), (256, 512, 'f16'), (64, 384, 'f16x3'), (256, 384, 'f16x3')])
 def test_eval_multi_pass_tile_cache_is_transparent(H, T, precision):
     """Shapes that need several passes over a member: with the optional workspace the weight tiles of pass 0 are
     cached and copied back; without it they are regenerated.  Both must give bit-identical fitness."""
@@ -148,6 +148,7 @@ def test_eval_multi_pass_tile_cache_is_transparent(H, T, precision):
     ref = orc.evaluate_population(th.cpu().numpy(), obs, target, 0.1, 1.0, 4, 1, 5, 8, d0, H, A)
     assert np.max(np.abs(b[:8].cpu().numpy() - ref) / np.abs(ref)) < (3e-5 if precision == 'f16x3' else 4e-3)
     assert ops().eval_workspace(d0, 64, A, 256, 'f16', DEV) is None          # single-pass shape: no scratch needed
+    assert ops().eval_workspace(d0, 256, A, 256, 'f16x3', DEV) is None       # one pass on a CTA pair
 
 
 def test_eval_state_generation_overrides_argument():
