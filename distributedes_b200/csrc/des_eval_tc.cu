@@ -156,7 +156,6 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
     using C = TcCfg<H, MODE, PAIR>;
     constexpr bool X3 = C::X3;
     constexpr int kNC = C::NC;
-    constexpr int kPeers = PAIR ? 2 : 1;
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;          // 0 = leader (issues the MMAs)
     constexpr int kEpiWarps = 8;              // NT == 2: four per tile slot; NT == 1: two per TMEM lane quadrant,
                                               // each taking one 32-column half of every accumulator chunk
@@ -174,12 +173,12 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
     const Layout L = a.L;
     const uint32_t gen = a.state ? (uint32_t)a.state->generation : a.gen;
 
-    // barriers the leader's MMA thread waits on collect arrivals from BOTH CTAs of a pair (remote arrive);
-    // barriers signalled by tcgen05.commit are multicast to both CTAs.
-    auto arrive_leader = [&](uint64_t *bar) {
-        if (PAIR && rank != 0) mbar_arrive_cluster(smem_u32(bar), 0);
-        else mbar_arrive(smem_u32(bar));
-    };
+    // Pairs: barriers signalled by tcgen05.commit are multicast to both CTAs.  Barriers the leader's MMA thread waits
+    // on (slot_full, acc_empty, h_ready) need the arrivals of BOTH CTAs: every warp arrives on its OWN CTA's barrier,
+    // and three forwarder lanes of the follower's (otherwise idle) MMA warp relay each completed phase to the leader
+    // with ONE cluster-scope arrive.  (Arriving remotely from every warp put a MEMBAR.GPU + ERRBAR — the lowering of
+    // mbarrier.arrive.release.cluster — into each generator/epilogue warp per slot: 10% of all stall samples.)
+    auto arrive_leader = [&](uint64_t *bar) { mbar_arrive(smem_u32(bar)); };
     auto commit = [&](uint64_t *bar) {
         if (PAIR) mma2_commit(smem_u32(bar));
         else mma_commit(smem_u32(bar));
@@ -187,17 +186,17 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
     if (warp == kMmaWarp) {
         if (lane == 0) {
             for (int s = 0; s < a.n_slots; ++s) {
-                mbar_init(smem_u32(&bars->slot_full[s]), kGenWarps * kPeers);
+                mbar_init(smem_u32(&bars->slot_full[s]), kGenWarps + ((PAIR && rank == 0) ? 1 : 0));
                 mbar_init(smem_u32(&bars->slot_empty[s]), 1);
             }
             for (int p = 0; p < 2; ++p) {
                 mbar_init(smem_u32(&bars->small_full[p]), kGenWarps);
                 mbar_init(smem_u32(&bars->small_empty[p]), n_epi_warps);
-                mbar_init(smem_u32(&bars->h_ready[p]), kWarpsPerSlot * kPeers);
+                mbar_init(smem_u32(&bars->h_ready[p]), kWarpsPerSlot + ((PAIR && rank == 0) ? 1 : 0));
                 mbar_init(smem_u32(&bars->h_free[p]), 1);
                 for (int st = 0; st < 2; ++st) {
                     mbar_init(smem_u32(&bars->acc_full[p][st]), 1);
-                    mbar_init(smem_u32(&bars->acc_empty[p][st]), kWarpsPerSlot * kPeers);
+                    mbar_init(smem_u32(&bars->acc_empty[p][st]), kWarpsPerSlot + ((PAIR && rank == 0) ? 1 : 0));
                 }
             }
             fence_barrier_init();
@@ -316,6 +315,29 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
                             }
                         }
                     }
+                }
+            }
+        }
+        if (PAIR && rank == 1 && lane < 3) {
+            // ---- follower CTA: relay completed local phases to the leader's barriers, in the leader's wait order
+            const int64_t rounds = (a.n_local - first + stride - 1) / stride * a.n_pass;     // (member, pass) pairs
+            if (lane == 0) {                      // slot_full: one relay per ring slot
+                uint32_t rs = 0, rph = 0;
+                for (int64_t i = 0; i < rounds * (C::NCH + C::NCH * C::KAT); ++i) {
+                    mbar_wait(smem_u32(&bars->slot_full[rs]), rph);
+                    mbar_arrive_cluster(smem_u32(&bars->slot_full[rs]), 0);
+                    if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
+                }
+            } else if (lane == 1) {               // acc_empty: one relay per accumulator-stage use
+                for (int64_t u = 0; u < rounds * 2 * C::NCH; ++u) {
+                    const uint32_t st = (uint32_t)u & 1, ph = (uint32_t)(u >> 1) & 1;
+                    mbar_wait(smem_u32(&bars->acc_empty[0][st]), ph);
+                    mbar_arrive_cluster(smem_u32(&bars->acc_empty[0][st]), 0);
+                }
+            } else {                              // h_ready: one relay per (member, pass)
+                for (int64_t v = 0; v < rounds; ++v) {
+                    mbar_wait(smem_u32(&bars->h_ready[0]), (uint32_t)v & 1);
+                    mbar_arrive_cluster(smem_u32(&bars->h_ready[0]), 0);
                 }
             }
         }
