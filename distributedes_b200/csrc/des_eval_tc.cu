@@ -668,19 +668,27 @@ static int launch_tc_nt(TcArgs &a, cudaStream_t st) {
     return DES_OK;
 }
 
-// Shapes whose two tiles do not fit one CTA's tensor memory (f16x3 at H = 256) run on CTA PAIRS: each CTA of a
-// 2-cluster keeps one tile and generates half of every weight tile (DES_TC_PAIR=0 falls back to two passes).
-static bool pair_enabled() {
+// CTA pairs (cta_group::2): each CTA of a 2-cluster keeps one tile and generates half of every weight tile.
+//   DES_TC_PAIR=1 (default)  pairs where two tiles do not fit one CTA's tensor memory (f16x3 at H = 256)
+//   DES_TC_PAIR=2            pairs wherever the shape allows it (H a multiple of 128, even number of tiles);
+//                            measured slower than two tile slots per CTA for f16 at H = 256 (10.3 vs 9.7 ms)
+//   DES_TC_PAIR=0            never (multi-pass with the L2 tile cache instead)
+static int pair_mode() {
     const char *e = getenv("DES_TC_PAIR");
-    return !(e && e[0] == '0');
+    if (!e) return 1;
+    return e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1);
 }
+static bool pair_enabled() { return pair_mode() != 0; }
 
 template <int H, int MODE>
 static int launch_tc(TcArgs &a, cudaStream_t st) {
     using C = TcCfg<H, MODE, false>;
     const int tiles = a.T / 128;
+    if constexpr (H % 128 == 0) {
+        const bool want = (C::NT_MAX < 2 && pair_mode() >= 1) || pair_mode() == 2;
+        if (tiles % 2 == 0 && want) return launch_tc_nt<H, MODE, 1, true>(a, st);
+    }
     if (C::NT_MAX >= 2 && tiles % 2 == 0) return launch_tc_nt<H, MODE, (C::NT_MAX >= 2 ? 2 : 1), false>(a, st);
-    if (C::NT_MAX < 2 && tiles % 2 == 0 && pair_enabled()) return launch_tc_nt<H, MODE, 1, true>(a, st);
     return launch_tc_nt<H, MODE, 1, false>(a, st);
 }
 
@@ -688,9 +696,10 @@ static void tc_shape(int H, bool x3, int T, int &n_pass, size_t &slot_bytes, int
     const int acols = x3 ? H : H / 2;
     const int nt_max = 512 / (acols + 2 * 64) >= 2 ? 2 : 1;
     const int n_tiles = T / 128;
-    const bool two_per_pass = n_tiles % 2 == 0 && (nt_max >= 2 || pair_enabled());
+    const bool pair = H % 128 == 0 && n_tiles % 2 == 0 && ((nt_max < 2 && pair_mode() >= 1) || pair_mode() == 2);
+    const bool two_per_pass = pair || (n_tiles % 2 == 0 && nt_max >= 2);
     n_pass = two_per_pass ? n_tiles / 2 : n_tiles;
-    const int nc = (nt_max < 2 && n_tiles % 2 == 0 && pair_enabled()) ? 128 : 64;
+    const int nc = pair ? 128 : 64;
     slot_bytes = (size_t)(x3 ? 2 : 1) * 64 * 128;
     slots_per_member = H / nc + (H / nc) * (H / 64);
 }
