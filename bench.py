@@ -31,6 +31,8 @@ sys.path.insert(0, REPO)
 
 import numpy as np  # noqa: E402
 
+EMIT = print
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -95,7 +97,7 @@ def run_reference(a):
                          'sample': r['sample']},
         'e2e': {'value': value, 'unit': 'policy-evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line), flush=True)
+    EMIT(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -308,14 +310,29 @@ def run_ours(a):
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches_per_step * a.steps,
             'roofline': roofline, 'cpu_baseline': cpu, 'other_modes': other,
         }
-        print(json.dumps(line), flush=True)
+        EMIT(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def _guard_stdout():
+    """Keep stdout clean for the ONE JSON line: anything libraries print on fd 1 (NCCL writes its version banner
+    there) goes to stderr; the JSON line is written to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real = os.fdopen(saved, 'w')
+
+    def emit(line):
+        real.write(line + '\n')
+        real.flush()
+    return emit
+
+
 if __name__ == '__main__':
     args = parse()
+    EMIT = _guard_stdout()
     if args.impl == 'reference':
         run_reference(args)
     else:

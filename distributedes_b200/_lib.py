@@ -44,6 +44,7 @@ SIGNATURES = {
     'des_obs_normalize': (C.c_int, [_P, _P, _P, _I32, _I32, _P]),
     'des_nes_eval_workspace_bytes': (_SZ, [Dims, C.c_int]),
     'des_nes_eval': (C.c_int, [_P, _P, _P, _P, Dims, _D, _D, _U64, _U64, _P, _I64, _I64, C.c_int, _P, _SZ, _P]),
+    'des_pop_eval': (C.c_int, [_P, _P, _P, _P, Dims, _D, _I64, _P]),
     'des_rank_workspace_bytes': (_SZ, [_I64]),
     'des_rank_workspace_bytes_n': (_SZ, [_I64, _I64]),
     'des_centered_rank': (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _P, _SZ, _P]),

@@ -23,7 +23,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 
 int eval_ffma_launch(float *fitness, const float *theta, const float *obs, const float *target, des_dims dims,
                      double sigma, double clip, uint64_t seed, uint64_t generation, const des_state *state,
-                     int64_t member_offset, int64_t n_local, cudaStream_t st);
+                     int64_t member_offset, int64_t n_local, const float *solutions, cudaStream_t st);
 int eval_tc_launch(float *fitness, const float *theta, const float *obs, const float *target, des_dims dims,
                    double sigma, double clip, uint64_t seed, uint64_t generation, const des_state *state,
                    int64_t member_offset, int64_t n_local, int precision, void *workspace, size_t workspace_bytes,
@@ -54,6 +54,19 @@ extern "C" DES_API int64_t des_param_count(int32_t d0, int32_t H, int32_t A) {
     return (int64_t)d0 * H + H + (int64_t)H * H + H + (int64_t)H * A + A;
 }
 
+extern "C" DES_API int des_pop_eval(float *fitness_out_dev, const float *solutions_dev, const float *obs_dev,
+                                    const float *target_dev, des_dims dims, double clip, int64_t n_solutions, void *stream) {
+    using namespace des;
+    DES_REQUIRE(dims.state_dim > 0 && dims.hidden > 0 && dims.action_dim > 0 && dims.tape_len > 0,
+                "des_pop_eval: bad dims (d0=%d H=%d A=%d T=%d)", dims.state_dim, dims.hidden, dims.action_dim, dims.tape_len);
+    DES_REQUIRE(n_solutions >= 0 && n_solutions < ((int64_t)1 << 31), "des_pop_eval: bad n_solutions");
+    DES_REQUIRE(clip >= 0.0, "des_pop_eval: clip must be >= 0");
+    if (n_solutions == 0) return DES_OK;
+    DES_REQUIRE(fitness_out_dev && solutions_dev && obs_dev && target_dev, "des_pop_eval: NULL pointer");
+    return eval_ffma_launch(fitness_out_dev, solutions_dev, obs_dev, target_dev, dims, 0.0, clip, 0, 0, nullptr, 0, n_solutions,
+                            solutions_dev, (cudaStream_t)stream);
+}
+
 extern "C" DES_API int des_nes_eval(float *fitness_out_dev, const float *theta_dev, const float *obs_dev, const float *target_dev,
                             des_dims dims, double sigma, double clip, uint64_t seed, uint64_t generation,
                             const des_state *state_dev, int64_t member_offset, int64_t n_local, int precision,
@@ -74,7 +87,7 @@ extern "C" DES_API int des_nes_eval(float *fitness_out_dev, const float *theta_d
     switch (precision) {
         case DES_FWD_FP32:
             return eval_ffma_launch(fitness_out_dev, theta_dev, obs_dev, target_dev, dims, sigma, clip, seed, generation,
-                                    state_dev, member_offset, n_local, st);
+                                    state_dev, member_offset, n_local, nullptr, st);
         case DES_FWD_F16:
         case DES_FWD_F16X3:
             return eval_tc_launch(fitness_out_dev, theta_dev, obs_dev, target_dev, dims, sigma, clip, seed, generation,

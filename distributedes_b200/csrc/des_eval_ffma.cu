@@ -20,6 +20,7 @@ constexpr int kObsPerWarp = kTileT / (kThreads / 32);
 struct EvalArgs {
     float *fitness;
     const float *theta, *obs, *target;
+    const float *solutions;   // FROM_MATRIX: [n_local][P] explicit weight vectors (cma_es.py:63-64 ships solutions), else NULL
     const des_state *state;
     Layout L;
     int T;
@@ -33,10 +34,15 @@ struct EvalArgs {
 __device__ __forceinline__ int round_up4(int x) { return (x + 3) & ~3; }
 
 // Generate theta'[off, off+cnt) into dst laid out as rows of K (row stride S); zero the K..Kp pad.
+// FROM_MATRIX: copy the member's explicit solution instead of perturbing theta.
+template <bool FROM_MATRIX>
 __device__ __forceinline__ void gen_rows(float *__restrict__ dst, const float *__restrict__ theta, int off, int R,
                                          int K, int Kp, int S, float sigma, uint32_t member, uint32_t gen,
                                          const PhiloxKey &key) {
     const int cnt = R * K;
+    if (FROM_MATRIX) {
+        for (int i = threadIdx.x; i < cnt; i += kThreads) dst[(i / K) * S + (i % K)] = __ldg(theta + off + i);
+    } else {
     const int qa = off >> 2, qb = (off + cnt - 1) >> 2;
     for (int q = qa + (int)threadIdx.x; q <= qb; q += kThreads) {
         const float4 z = noise_quad((uint32_t)q, member, gen, kStreamNesEps, key);
@@ -52,6 +58,7 @@ __device__ __forceinline__ void gen_rows(float *__restrict__ dst, const float *_
             }
         }
     }
+    }
     if (Kp > K) {
         const int pad = Kp - K;
         for (int i = threadIdx.x; i < kRows * pad; i += kThreads) dst[(i / pad) * S + K + (i % pad)] = 0.f;
@@ -60,6 +67,7 @@ __device__ __forceinline__ void gen_rows(float *__restrict__ dst, const float *_
     for (int i = R * Kp + threadIdx.x; i < kRows * Kp; i += kThreads) dst[(i / Kp) * S + (i % Kp)] = 0.f;
 }
 
+template <bool FROM_MATRIX>
 __global__ void __launch_bounds__(kThreads) eval_ffma_kernel(EvalArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int S = a.S;
@@ -73,6 +81,7 @@ __global__ void __launch_bounds__(kThreads) eval_ffma_kernel(EvalArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t gen = a.state ? (uint32_t)a.state->generation : a.gen;
     const uint32_t member = (uint32_t)(a.member_offset + blockIdx.x);
+    const float *wsrc = FROM_MATRIX ? a.solutions + (int64_t)blockIdx.x * L.P : a.theta;
     double fit = 0.0;                       // meaningful in thread 0 only
 
     for (int t0 = 0; t0 < a.T; t0 += kTileT) {
@@ -97,18 +106,22 @@ __global__ void __launch_bounds__(kThreads) eval_ffma_kernel(EvalArgs a) {
                 const int R = min(kRows, Nout - n0);
                 __syncthreads();            // previous chunk's readers of Ws/bias (and obs load) done
                 if (R > 0) {
-                    gen_rows(Ws, a.theta, off_w + n0 * K, R, K, Kp, S, a.sigma, member, gen, a.key);
+                    gen_rows<FROM_MATRIX>(Ws, wsrc, off_w + n0 * K, R, K, Kp, S, a.sigma, member, gen, a.key);
                     // biases of the chunk: off_b + n0 .. + R
                     const int ob = off_b + n0;
-                    const int qa = ob >> 2, qb = (ob + R - 1) >> 2;
-                    for (int q = qa + (int)threadIdx.x; q <= qb; q += kThreads) {
-                        const float4 z = noise_quad((uint32_t)q, member, gen, kStreamNesEps, a.key);
-                        const float zz[4] = {z.x, z.y, z.z, z.w};
+                    if (FROM_MATRIX) {
+                        for (int i = threadIdx.x; i < R; i += kThreads) bias[i] = __ldg(wsrc + ob + i);
+                    } else {
+                        const int qa = ob >> 2, qb = (ob + R - 1) >> 2;
+                        for (int q = qa + (int)threadIdx.x; q <= qb; q += kThreads) {
+                            const float4 z = noise_quad((uint32_t)q, member, gen, kStreamNesEps, a.key);
+                            const float zz[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int local = 4 * q + e - ob;
-                            if (local >= 0 && local < R)
-                                bias[local] = __fmaf_rn(a.sigma, zz[e], __ldg(a.theta + ob + local));
+                            for (int e = 0; e < 4; ++e) {
+                                const int local = 4 * q + e - ob;
+                                if (local >= 0 && local < R)
+                                    bias[local] = __fmaf_rn(a.sigma, zz[e], __ldg(a.theta + ob + local));
+                            }
                         }
                     }
                 }
@@ -169,8 +182,9 @@ __global__ void __launch_bounds__(kThreads) eval_ffma_kernel(EvalArgs a) {
 
 int eval_ffma_launch(float *fitness, const float *theta, const float *obs, const float *target, des_dims dims,
                      double sigma, double clip, uint64_t seed, uint64_t generation, const des_state *state,
-                     int64_t member_offset, int64_t n_local, cudaStream_t st) {
+                     int64_t member_offset, int64_t n_local, const float *solutions, cudaStream_t st) {
     EvalArgs a;
+    a.solutions = solutions;
     a.fitness = fitness; a.theta = theta; a.obs = obs; a.target = target; a.state = state;
     a.L = Layout(dims.state_dim, dims.hidden, dims.action_dim);
     a.T = dims.tape_len;
@@ -186,8 +200,13 @@ int eval_ffma_launch(float *fitness, const float *theta, const float *obs, const
         set_error("des_nes_eval(FP32): hidden/state_dim %d needs %zu B shared memory (> 227 KB)", kmax, smem);
         return DES_ERR_UNSUPPORTED;
     }
-    DES_CUDA(cudaFuncSetAttribute(eval_ffma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    eval_ffma_kernel<<<(unsigned)n_local, kThreads, smem, st>>>(a);
+    if (solutions) {
+        DES_CUDA(cudaFuncSetAttribute(eval_ffma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        eval_ffma_kernel<true><<<(unsigned)n_local, kThreads, smem, st>>>(a);
+    } else {
+        DES_CUDA(cudaFuncSetAttribute(eval_ffma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        eval_ffma_kernel<false><<<(unsigned)n_local, kThreads, smem, st>>>(a);
+    }
     DES_LAUNCH_CHECK("eval_ffma_kernel");
     return DES_OK;
 }

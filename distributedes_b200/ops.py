@@ -147,6 +147,22 @@ def nes_eval(theta, obs, target, *, hidden, sigma, clip, seed, generation=0, sta
     return out
 
 
+def pop_eval(solutions, obs, target, *, hidden, clip, out=None):
+    """Tape fitness of explicit weight vectors solutions[n, P] (what CMA-ES evaluates, cma_es.py:62-75)."""
+    T, d0 = obs.shape
+    A = target.shape[1]
+    n, P = solutions.shape
+    if P != param_count(d0, hidden, A):
+        raise RuntimeError('solutions have %d entries, the (%d,%d,%d) MLP needs %d' % (P, d0, hidden, A, param_count(d0, hidden, A)))
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=solutions.device)
+    with _on(solutions, 'solutions'):
+        _lib.check(_lib.load().des_pop_eval(_ptr(out, torch.float32, 'out'), _ptr(solutions, torch.float32, 'solutions'),
+                                            _ptr(obs, torch.float32, 'obs'), _ptr(target, torch.float32, 'target'),
+                                            Dims(d0, hidden, A, T), clip, n, _stream()), 'des_pop_eval')
+    return out
+
+
 def rank_workspace(n_local, device, N=None):
     lib = _lib.load()
     nbytes = lib.des_rank_workspace_bytes_n(N, n_local) if N is not None else lib.des_rank_workspace_bytes(n_local)

@@ -137,6 +137,12 @@ DES_API int des_nes_eval(float *fitness_out_dev, const float *theta_dev, const f
                  int64_t n_local, int precision, void *workspace_dev, size_t workspace_bytes,
                  void *stream);
 
+/* fitness_out_dev[i] = the same tape fitness for EXPLICIT weight vectors solutions_dev[n_solutions][P] (no noise):
+ * the evaluation CMA-ES needs, where the master ships sampled solutions to the workers (cma_es.py:62-64,
+ * Worker.run cma_es.py:22-29 -> Evaluator.eval utils.py:116-124).  fp32 CUDA-core path, any shape. */
+DES_API int des_pop_eval(float *fitness_out_dev, const float *solutions_dev, const float *obs_dev,
+                 const float *target_dev, des_dims dims, double clip, int64_t n_solutions, void *stream);
+
 /* ---- centered-rank shaping ------------------------------------------------------------------ */
 
 /* For the n_local members starting at member_offset of the GLOBAL fitness vector fitness_all_dev[N]:
