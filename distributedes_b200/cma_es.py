@@ -1,0 +1,160 @@
+"""CMA-ES with the reference's surface (cma_es.py:13-111): Worker / train() / test(), and the strategy object the
+reference takes from the third-party `cma` package (cma.CMAEvolutionStrategy, cma_es.py:49: ask() :62, tell() :90).
+
+The hot arithmetic — the rank-mu covariance update inside tell() — is des_cma_rank_mu + des_cma_cov_apply
+(csrc/des_cma.cu); solutions are evaluated by des_pop_eval and rank-shaped by des_centered_rank.  The small
+O(n)/O(n^2) bookkeeping around it (mean, evolution paths, step size) and the library calls a CMA step needs
+(the [lambda,n]x[n,n] sampling GEMM and the symmetric eigendecomposition) go through torch (cuBLAS / cuSOLVER):
+plumbing, not kernels of this repo.  Equations: Hansen's tutorial arXiv:1604.00772 (cited at README.md:16);
+pycma itself is not available here, so this follows oracle/cma_oracle.py's restatement ("parity unpinned").
+"""
+from __future__ import annotations
+
+import sys
+import time
+
+import numpy as np
+import torch
+
+from . import ops
+from .utils import StaticNormalizer, logger
+
+
+def cma_constants(n, lam):
+    """Default strategy parameters, tutorial Table 1 (positive weights)."""
+    wp = np.log((lam + 1) / 2.0) - np.log(np.arange(1, lam + 1))
+    mu = lam // 2
+    mu_eff = wp[:mu].sum() ** 2 / (wp[:mu] ** 2).sum()
+    cc = (4 + mu_eff / n) / (n + 4 + 2 * mu_eff / n)
+    c1 = 2.0 / ((n + 1.3) ** 2 + mu_eff)
+    cmu = min(1 - c1, 2.0 * (0.25 + mu_eff + 1 / mu_eff - 2) / ((n + 2) ** 2 + mu_eff))
+    cs = (mu_eff + 2) / (n + mu_eff + 5)
+    ds = 1 + 2 * max(0.0, np.sqrt((mu_eff - 1) / (n + 1)) - 1) + cs
+    w = np.zeros(lam)
+    w[:mu] = wp[:mu] / wp[:mu].sum()
+    return dict(w=w, mu=mu, mu_eff=mu_eff, cc=cc, c1=c1, cmu=cmu, cs=cs, ds=ds)
+
+
+class CMAEvolutionStrategy:
+    """GPU-resident (mu/mu_w, lambda)-CMA-ES.  C is fp32 (the rank-mu kernel's type); the vectors and the
+    eigen-system are fp64."""
+
+    def __init__(self, x0, sigma0, popsize, seed=0, device=None):
+        self.device = torch.device(device if device is not None else ('cuda:%d' % torch.cuda.current_device()))
+        if self.device.type != 'cuda':
+            raise RuntimeError('distributedes_b200.cma_es needs a CUDA device: there is no CPU fallback')
+        self.n, self.lam, self.seed = len(x0), int(popsize), int(seed)
+        k = cma_constants(self.n, self.lam)
+        self.k = k
+        dev, f64 = self.device, torch.float64
+        self.w64 = torch.tensor(k['w'], dtype=f64, device=dev)
+        self.w32 = self.w64.to(torch.float32).contiguous()
+        self.m = torch.tensor(np.asarray(x0, dtype=np.float64), device=dev)
+        self.sigma = float(sigma0)
+        self.C = torch.eye(self.n, dtype=torch.float32, device=dev)
+        self.dC = torch.empty_like(self.C)
+        self.pc = torch.zeros(self.n, dtype=f64, device=dev)
+        self.ps = torch.zeros(self.n, dtype=f64, device=dev)
+        self.B = torch.eye(self.n, dtype=f64, device=dev)
+        self.D = torch.ones(self.n, dtype=f64, device=dev)
+        self.gen = 0
+        self.chiN = np.sqrt(self.n) * (1 - 1.0 / (4 * self.n) + 1.0 / (21 * self.n * self.n))
+
+    def ask(self, z=None):
+        """lambda solutions x_i = m + sigma*B*D*z_i (cma_es.py:62).  z defaults to the counter noise stream
+        (Philox, stream tag 1, counter = (j/4, member, generation)), so shards can regenerate it."""
+        if z is None:
+            z = ops.noise_fill(self.lam, self.n, self.seed, self.gen, stream_tag=1, device=self.device)
+        self.z = z
+        BD = (self.B * self.D).to(torch.float32)                 # columns scaled by D
+        y = z.to(torch.float32) @ BD.T                           # [lambda, n] x [n, n]  (library GEMM)
+        self.X = (self.m + self.sigma * y.to(torch.float64)).to(torch.float32).contiguous()
+        return self.X
+
+    def tell(self, solutions, cost):
+        """cma_es.py:90.  solutions [lambda, n] (as returned by ask), cost [lambda] (lower is better; rank-shaped or
+        raw — only the order matters)."""
+        k, n = self.k, self.n
+        cost = torch.as_tensor(cost, device=self.device, dtype=torch.float64).reshape(-1)
+        order = torch.sort(cost, stable=True).indices
+        X = torch.as_tensor(solutions, device=self.device)
+        Y = ((X[order].to(torch.float64) - self.m) / self.sigma)            # y_{i:lambda}
+        yw = self.w64 @ Y
+        self.m = self.m + self.sigma * yw
+        cs, ds, cc, c1, cmu, mu_eff = k['cs'], k['ds'], k['cc'], k['c1'], k['cmu'], k['mu_eff']
+        cinv_yw = self.B @ ((self.B.T @ yw) / self.D)
+        self.ps = (1 - cs) * self.ps + np.sqrt(cs * (2 - cs) * mu_eff) * cinv_yw
+        norm_ps = float(torch.linalg.norm(self.ps))
+        hsig = float(norm_ps / np.sqrt(1 - (1 - cs) ** (2 * (self.gen + 1))) / self.chiN < 1.4 + 2.0 / (n + 1))
+        self.pc = (1 - cc) * self.pc + hsig * np.sqrt(cc * (2 - cc) * mu_eff) * yw
+        # ---- the hot part: rank-mu term and covariance update on our kernels (fp32)
+        ops.cma_rank_mu(Y.to(torch.float32).contiguous(), self.w32, out=self.dC)
+        decay = 1 + c1 * (1 - hsig) * cc * (2 - cc) - c1 - cmu * float(k['w'].sum())
+        ops.cma_cov_apply(self.C, self.dC, self.pc.to(torch.float32).contiguous(), decay=decay, c1=c1, cmu=cmu)
+        self.sigma = self.sigma * float(np.exp((cs / ds) * (norm_ps / self.chiN - 1)))
+        d2, self.B = torch.linalg.eigh(self.C.to(torch.float64))            # library eigendecomposition (cuSOLVER)
+        self.D = torch.sqrt(torch.clamp(d2, min=1e-300))
+        self.gen += 1
+        return order
+
+
+class Worker:
+    """cma_es.py:13-29 re-cast: evaluates a batch of shipped solutions on one GPU (des_pop_eval)."""
+
+    def __init__(self, id, state_normalizer, task_q, result_q, stop, config, device=None):
+        self.id, self.config = id, config
+        self.device = torch.device(device if device is not None else ('cuda:%d' % torch.cuda.current_device()))
+        env = config.env_fn()
+        self.T = env.tape_len
+        self.obs = torch.from_numpy(env.obs).to(self.device)
+        self.target = torch.from_numpy(env.target).to(self.device)
+
+    def run(self, solutions):
+        """fitness (= cost, cma_es.py:28: Evaluator.eval returns -mean return) of every solution."""
+        fit = ops.pop_eval(solutions, self.obs, self.target, hidden=self.config.hidden_size, clip=self.config.clip)
+        return -fit
+
+
+def train(config):
+    """cma_es.py:31-100.  Returns [training_rewards, training_steps, training_timestamps]."""
+    worker = Worker(0, StaticNormalizer(config.state_dim), None, None, None, config)
+    es = CMAEvolutionStrategy(config.initial_weight, config.sigma, config.pop_size, seed=getattr(config, 'seed', 0),
+                              device=worker.device)
+    total_steps = 0
+    initial_time = time.time()
+    training_rewards, training_steps, training_timestamps = [], [], []
+    test_mean, test_ste = test(config, config.initial_weight, None, worker=worker)           # :56
+    logger.info('total steps %d, %f(%f)' % (total_steps, test_mean, test_ste))
+    training_rewards.append(test_mean)
+    training_steps.append(0)
+    training_timestamps.append(0)
+    generation = 0
+    while True:
+        solutions = es.ask()                                                                # :62
+        cost = worker.run(solutions)                                                        # :63-72
+        total_steps += config.pop_size * config.repetitions * worker.T                      # :73
+        best = int(torch.argmin(cost))                                                      # :75
+        elapsed_time = time.time() - initial_time
+        test_mean, test_ste = test(config, solutions[best], None, worker=worker)            # :77
+        logger.info('total steps %d, test %f(%f), best %f, elapased time %f' %
+                    (total_steps, test_mean, test_ste, -float(cost.min()), elapsed_time))
+        training_rewards.append(test_mean)
+        training_steps.append(total_steps)
+        training_timestamps.append(elapsed_time)
+        generation += 1
+        if config.max_steps and total_steps > config.max_steps:                             # :85-87
+            break
+        if getattr(config, 'max_generations', 0) and generation >= config.max_generations:
+            break
+        shaped = ops.centered_rank(cost.to(torch.float32).contiguous())                     # :89 fitness_shift(cost)
+        es.tell(solutions, shaped)                                                          # :90
+    return [training_rewards, training_steps, training_timestamps]
+
+
+def test(config, solution, stats, worker=None):
+    """cma_es.py:102-111 (which divides the std by config.repetitions, not test_repetitions)."""
+    worker = worker if worker is not None else Worker(0, StaticNormalizer(config.state_dim), None, None, None, config)
+    sol = torch.as_tensor(np.asarray(solution.detach().cpu() if isinstance(solution, torch.Tensor) else solution,
+                                     dtype=np.float32)).reshape(1, -1).to(worker.device)
+    rewards = [float(-worker.run(sol)[0]) for _ in range(config.test_repetitions)]
+    return np.mean(rewards), np.std(rewards) / config.repetitions

@@ -12,16 +12,19 @@ namespace des {
 constexpr int kCmaThreads = 256;
 constexpr int kCmaKP = 16;   // members per k-panel
 
-// TILE x TILE outputs per CTA, 256 threads as 16x16, each (TILE/16)^2 outputs strided by 16 so that
-// shared-memory reads are conflict-free broadcasts/rows.
+// TILE x TILE outputs per CTA, 256 threads as 16 x 16.  Each thread owns (TILE/16)^2 outputs arranged as blocks of
+// 4 consecutive rows/columns spaced 64 apart (rows ty*4 + {0..3} + 64*g), so every shared-memory operand read is one
+// conflict-free LDS.128 (16 FMA per LDS for the 128 tile).  k-panels of 16 members are double buffered: the next
+// panel's global loads are in flight while the current one is multiplied.
 template <int TILE>
 __global__ void __launch_bounds__(kCmaThreads) cma_rank_mu_kernel(float *__restrict__ dC, const float *__restrict__ Y,
                                                                   const float *__restrict__ w, int64_t lambda, int64_t n,
                                                                   int tiles_per_side) {
-    constexpr int MT = TILE / 16;
-    __shared__ float As[kCmaKP][TILE + 4];   // w_k * Y[k][i0 + i]
-    __shared__ float Bs[kCmaKP][TILE + 4];   //       Y[k][j0 + j]
-    // linear block id -> (bi <= bj) upper-triangular tile
+    constexpr int G = TILE / 64;                 // 4-wide groups per thread and dimension (1 or 2)
+    constexpr int MT = 4 * G;
+    constexpr int LD = kCmaKP * TILE / kCmaThreads;   // elements each thread stages per operand and panel
+    __shared__ __align__(16) float As[2][kCmaKP][TILE];   // w_k * Y[k][i0 + i]
+    __shared__ __align__(16) float Bs[2][kCmaKP][TILE];   //       Y[k][j0 + j]
     int bi = 0, rem = blockIdx.x;
     while (rem >= tiles_per_side - bi) { rem -= tiles_per_side - bi; ++bi; }
     const int bj = bi + rem;
@@ -34,8 +37,11 @@ __global__ void __launch_bounds__(kCmaThreads) cma_rank_mu_kernel(float *__restr
 #pragma unroll
         for (int b = 0; b < MT; ++b) acc[a][b] = 0.f;
 
-    for (int64_t k0 = 0; k0 < lambda; k0 += kCmaKP) {
-        for (int idx = threadIdx.x; idx < kCmaKP * TILE; idx += kCmaThreads) {
+    float ra[LD], rb[LD];
+    auto fetch = [&](int64_t k0) {
+#pragma unroll
+        for (int e = 0; e < LD; ++e) {
+            const int idx = threadIdx.x + e * kCmaThreads;
             const int kk = idx / TILE, c = idx - kk * TILE;
             const int64_t k = k0 + kk;
             float a = 0.f, b = 0.f;
@@ -44,30 +50,53 @@ __global__ void __launch_bounds__(kCmaThreads) cma_rank_mu_kernel(float *__restr
                 if (i0 + c < n) a = wk * __ldg(Y + k * n + i0 + c);
                 if (j0 + c < n) b = __ldg(Y + k * n + j0 + c);
             }
-            As[kk][c] = a;
-            Bs[kk][c] = b;
+            ra[e] = a;
+            rb[e] = b;
         }
-        __syncthreads();
+    };
+    auto stage = [&](int buf) {
+#pragma unroll
+        for (int e = 0; e < LD; ++e) {
+            const int idx = threadIdx.x + e * kCmaThreads;
+            const int kk = idx / TILE, c = idx - kk * TILE;
+            As[buf][kk][c] = ra[e];
+            Bs[buf][kk][c] = rb[e];
+        }
+    };
+    fetch(0);
+    stage(0);
+    __syncthreads();
+    int buf = 0;
+    for (int64_t k0 = 0; k0 < lambda; k0 += kCmaKP) {
+        const bool more = k0 + kCmaKP < lambda;
+        if (more) fetch(k0 + kCmaKP);            // global loads overlap the multiply below
 #pragma unroll
         for (int kk = 0; kk < kCmaKP; ++kk) {
             float av[MT], bv[MT];
 #pragma unroll
-            for (int a = 0; a < MT; ++a) av[a] = As[kk][ty + 16 * a];
-#pragma unroll
-            for (int b = 0; b < MT; ++b) bv[b] = Bs[kk][tx + 16 * b];
+            for (int g = 0; g < G; ++g) {
+                const float4 a4 = *reinterpret_cast<const float4 *>(&As[buf][kk][ty * 4 + 64 * g]);
+                const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[buf][kk][tx * 4 + 64 * g]);
+                av[4 * g] = a4.x; av[4 * g + 1] = a4.y; av[4 * g + 2] = a4.z; av[4 * g + 3] = a4.w;
+                bv[4 * g] = b4.x; bv[4 * g + 1] = b4.y; bv[4 * g + 2] = b4.z; bv[4 * g + 3] = b4.w;
+            }
 #pragma unroll
             for (int a = 0; a < MT; ++a)
 #pragma unroll
                 for (int b = 0; b < MT; ++b) acc[a][b] = __fmaf_rn(av[a], bv[b], acc[a][b]);
         }
-        __syncthreads();
+        if (more) {
+            stage(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
     }
 #pragma unroll
     for (int a = 0; a < MT; ++a) {
-        const int64_t i = i0 + ty + 16 * a;
+        const int64_t i = i0 + ty * 4 + (a & 3) + 64 * (a >> 2);
 #pragma unroll
         for (int b = 0; b < MT; ++b) {
-            const int64_t j = j0 + tx + 16 * b;
+            const int64_t j = j0 + tx * 4 + (b & 3) + 64 * (b >> 2);
             if (i < n && j < n) {
                 if (bi != bj) {
                     dC[i * n + j] = acc[a][b];

@@ -61,3 +61,52 @@ def cov_update(C, dC, pc, c1, cmu, sum_w, hsig=1.0, cc=0.0):
 
 def sphere(X):
     return (np.asarray(X, dtype=np.float64) ** 2).sum(axis=-1)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# One full CMA-ES generation — still a restatement of the tutorial, still parity-UNPINNED.
+# ----------------------------------------------------------------------------------------------------------------
+class CMAState:
+    """(mu/mu_w, lambda)-CMA-ES, tutorial arXiv:1604.00772 Fig. 6 / eqs. 38-47 with the Table 1 defaults, positive
+    weights, c_m = 1, eigendecomposition refreshed every generation.  Stands in for cma.CMAEvolutionStrategy
+    (cma_es.py:49) with ask() (:62) and tell() (:90).  fp64 throughout."""
+
+    def __init__(self, x0, sigma0, lam):
+        self.n = n = len(x0)
+        self.lam = lam
+        self.k = cma_constants(n, lam)
+        self.m = np.asarray(x0, dtype=np.float64).copy()
+        self.sigma = float(sigma0)
+        self.C = np.eye(n)
+        self.pc = np.zeros(n)
+        self.ps = np.zeros(n)
+        self.B = np.eye(n)
+        self.D = np.ones(n)
+        self.gen = 0
+        self.chiN = np.sqrt(n) * (1 - 1.0 / (4 * n) + 1.0 / (21 * n * n))
+
+    def ask(self, z):
+        """x_i = m + sigma * B D z_i (eq. 38-40); z [lambda, n] standard normal."""
+        self.Y = (np.asarray(z, dtype=np.float64) * self.D) @ self.B.T
+        return self.m + self.sigma * self.Y
+
+    def tell(self, X, cost):
+        k, n = self.k, self.n
+        w, mu_eff, cc, c1, cmu, cs, ds = k['w'], k['mu_eff'], k['cc'], k['c1'], k['cmu'], k['cs'], k['ds']
+        Y, order = sort_and_scale(X, cost, self.m, self.sigma)
+        yw = w @ Y                                                       # eq. 41
+        self.m = self.m + self.sigma * yw                                # eq. 42 (c_m = 1)
+        Cinvsqrt_yw = self.B @ ((self.B.T @ yw) / self.D)
+        self.ps = (1 - cs) * self.ps + np.sqrt(cs * (2 - cs) * mu_eff) * Cinvsqrt_yw          # eq. 43
+        norm_ps = np.linalg.norm(self.ps)
+        hsig = float(norm_ps / np.sqrt(1 - (1 - cs) ** (2 * (self.gen + 1))) / self.chiN < 1.4 + 2.0 / (n + 1))
+        self.pc = (1 - cc) * self.pc + hsig * np.sqrt(cc * (2 - cc) * mu_eff) * yw            # eq. 45
+        dC = rank_mu_delta(Y, w)
+        self.C, self.decay = cov_update(self.C, dC, self.pc, c1, cmu, w.sum(), hsig=hsig, cc=cc)   # eq. 47
+        self.dC = dC
+        self.sigma = self.sigma * np.exp((cs / ds) * (norm_ps / self.chiN - 1))               # eq. 44
+        self.C = 0.5 * (self.C + self.C.T)
+        d2, self.B = np.linalg.eigh(self.C)
+        self.D = np.sqrt(np.maximum(d2, 1e-300))
+        self.gen += 1
+        return order

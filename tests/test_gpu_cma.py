@@ -73,3 +73,57 @@ def test_rank_mu_eight_shards_of_baseline_config5():
     for r in range(8):
         total += ops.cma_rank_mu(Yt[r * 128:(r + 1) * 128].contiguous(), wt[r * 128:(r + 1) * 128].contiguous())
     both_norms(total.cpu().numpy(), ref)
+
+
+def test_full_cma_generation_matches_restatement():
+    """BASELINE configs[2]: sphere, n=1024, lambda=256, sigma0=1 (cma_es.py:147): three generations of
+    distributedes_b200.cma_es.CMAEvolutionStrategy against the fp64 restatement.  Both tell() the SAME solutions
+    (sampled by the restatement): x = m + sigma*B*D*z depends on the eigenvectors' signs / rotation inside
+    near-degenerate eigenspaces, which no two eigensolvers agree on, so ask() is checked against the strategy's
+    own B, D instead."""
+    from distributedes_b200.cma_es import CMAEvolutionStrategy
+    n, lam = 1024, 256
+    rs = np.random.RandomState(0)
+    m0 = rs.randn(n)
+    es = CMAEvolutionStrategy(m0, 1.0, lam, seed=9, device=DEV)
+    ref = cma.CMAState(m0, 1.0, lam)
+    for gen in range(3):
+        X = es.ask()                                                   # z from the counter noise stream (tag 1)
+        z = es.z.cpu().numpy().astype(np.float64)
+        B, D = es.B.cpu().numpy(), es.D.cpu().numpy()
+        own = es.m.cpu().numpy() + es.sigma * ((z * D) @ B.T)          # eq. 38-40 with the strategy's own eigen-system
+        assert np.max(np.abs(X.cpu().numpy() - own)) <= 2e-5 * np.max(np.abs(own))      # fp32 sampling GEMM
+        if gen == 0:                                                   # B = I, D = 1: also equals the restatement's ask
+            assert np.max(np.abs(X.cpu().numpy() - ref.ask(z))) <= 2e-5 * np.max(np.abs(own))
+        Xr = ref.ask(rs.randn(lam, n)).astype(np.float32)              # common solutions, exactly representable in fp32
+        cost = cma.sphere(Xr)
+        es.tell(torch.from_numpy(Xr).to(DEV), torch.from_numpy(cost))
+        ref.tell(Xr.astype(np.float64), cost)
+        both_norms(es.dC.cpu().numpy(), ref.dC)
+        both_norms(es.C.cpu().numpy(), ref.C)
+        assert np.linalg.norm(es.m.cpu().numpy() - ref.m) <= 1e-6 * np.linalg.norm(ref.m)
+        assert abs(es.sigma - ref.sigma) <= 1e-6 * ref.sigma
+        assert np.linalg.norm(es.pc.cpu().numpy() - ref.pc) <= 1e-6 * np.linalg.norm(ref.pc)
+        assert np.linalg.norm(es.ps.cpu().numpy() - ref.ps) <= 1e-4 * np.linalg.norm(ref.ps)   # through fp32 C
+        # the eigen-system reproduces C
+        Crec = (es.B * es.D ** 2) @ es.B.T
+        assert float((Crec - es.C.double()).abs().max()) <= 1e-9
+    assert es.sigma < 1.0 and cma.sphere(ref.m[None])[0] < cma.sphere(m0[None])[0]     # it is actually optimising
+
+
+def test_pop_eval_and_cma_train_surface():
+    """des_pop_eval == des_nes_eval(sigma=0) for explicit solutions; cma_es.train keeps the reference's return triple."""
+    from distributedes_b200 import cma_es, ops
+    from distributedes_b200.config import BipedalWalkerConfig
+    from oracle import nes_oracle as orc
+    cfg = BipedalWalkerConfig(hidden_size=16, tape_len=64)            # cma_es.py:129 uses hidden 16
+    cfg.pop_size, cfg.sigma, cfg.max_generations = 64, 1.0, 3
+    env = cfg.env_fn()
+    sols = np.stack([cfg.initial_weight + 0.05 * np.random.RandomState(i).randn(len(cfg.initial_weight)) for i in range(5)]).astype(np.float32)
+    fit = ops.pop_eval(torch.from_numpy(sols).to(DEV), torch.from_numpy(env.obs).to(DEV), torch.from_numpy(env.target).to(DEV),
+                       hidden=16, clip=1.0).cpu().numpy()
+    ref = orc.tape_fitness(orc.forward(sols, env.obs, 24, 16, 4), env.target, 1.0)
+    assert np.max(np.abs(fit - ref) / np.abs(ref)) < 2e-5
+    rewards, steps, stamps = cma_es.train(cfg)
+    assert len(rewards) == len(steps) == len(stamps) == 4 and steps[0] == 0 and steps[1] == 64 * 64
+    assert np.all(np.isfinite(rewards)) and np.all(np.diff(stamps) >= 0)

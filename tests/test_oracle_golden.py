@@ -162,3 +162,20 @@ def test_generations_with_reference_normaliser_on(golden_dir, tag):
     g0 = load(golden_dir, 'train_%s.npz' % tag)
     assert np.allclose(g['grad_after_wd'][0], g0['grad_after_wd'][0])
     assert not np.allclose(g['grad_after_wd'][1], g0['grad_after_wd'][1], rtol=1e-3)
+
+
+def test_cma_restatement_is_a_working_cma_es():
+    """The CMA oracle is unpinned (no pycma, no fixtures in the reference): at least it must behave like CMA-ES —
+    weights/constants as in the tutorial's Table 1 and monotone progress on the sphere."""
+    from oracle import cma_oracle as cma
+    k = cma.cma_constants(1024, 256)
+    assert k['mu'] == 128 and abs(k['w'].sum() - 1) < 1e-12 and np.all(np.diff(k['w'][:128]) < 0)
+    assert 60 < k['mu_eff'] < 80 and 0 < k['c1'] < k['cmu'] < 1 and k['c1'] + k['cmu'] <= 1
+    rs = np.random.RandomState(0)
+    st = cma.CMAState(rs.randn(32), 1.0, 16)
+    f0 = cma.sphere(st.m[None])[0]
+    for _ in range(60):
+        X = st.ask(rs.randn(16, 32))
+        st.tell(X, cma.sphere(X))
+        assert np.allclose(st.C, st.C.T) and np.all(st.D > 0)
+    assert cma.sphere(st.m[None])[0] < 0.05 * f0
