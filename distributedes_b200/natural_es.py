@@ -8,6 +8,9 @@ train(config) in each; with torch.distributed uninitialised it is a single-GPU r
 """
 from __future__ import annotations
 
+import logging
+import os
+import pickle
 import time
 
 import numpy as np
@@ -119,3 +122,59 @@ def launch(config_fn, world_size, port=29533):
     result = ctx.SimpleQueue()
     mp.spawn(_launch_entry, args=(world_size, config_fn, port, result), nprocs=world_size, join=True)
     return result.get()
+
+
+# ---- run bookkeeping (natural_es.py:113-124) ----------------------------------------------------------
+def multi_runs(config, runs=10, log_dir='log', data_dir='data'):
+    """natural_es.py:113-124: `runs` sequential train() runs, a per-task log file and the pickle of
+    [[rewards, steps, timestamps], ...] rewritten after every run — same file names and on-disk format as the reference
+    (its plotting scripts read data/<tag>-stats-<task>.bin).  Unlike the reference the directories are created, and the
+    optimiser state does not leak from one run to the next (natural_es.py:120-122 reuses config.opt)."""
+    os.makedirs(log_dir, exist_ok=True)
+    os.makedirs(data_dir, exist_ok=True)
+    fh = logging.FileHandler(os.path.join(log_dir, '%s-%s.txt' % (config.tag, config.task)))
+    fh.setLevel(logging.DEBUG)
+    logger.addHandler(fh)
+    stats = []
+    try:
+        for run in range(runs):
+            logger.info('Run %d' % (run))
+            stats.append(train(config))
+            with open(os.path.join(data_dir, '%s-stats-%s.bin' % (config.tag, config.task)), 'wb') as f:
+                pickle.dump(stats, f)
+    finally:
+        logger.removeHandler(fh)
+        fh.close()
+    return stats
+
+
+def save_checkpoint(engine, path):
+    """Everything a run needs to resume: theta, Adam (m, v, beta^t, t), generation counter, observation statistics,
+    seed.  (The reference keeps no training checkpoint)"""
+    from . import ops
+    st = ops.read_state(engine.state)
+    blob = dict(theta=engine.theta_numpy(), adam_m=engine.adam_m.cpu().numpy(), adam_v=engine.adam_v.cpu().numpy(),
+                state=st, seed=engine.seed, pop_size=engine.N, dims=(engine.d0, engine.H, engine.A),
+                obs_stats=engine.obs_stats.cpu().numpy() if engine.normalize_obs else None)
+    with open(path, 'wb') as f:
+        pickle.dump(blob, f)
+
+
+def load_checkpoint(engine, path):
+    """Restore a checkpoint written by save_checkpoint into a compatible engine (same MLP dims and population)."""
+    import ctypes as C
+    from ._lib import State
+    with open(path, 'rb') as f:
+        blob = pickle.load(f)
+    if tuple(blob['dims']) != (engine.d0, engine.H, engine.A) or blob['pop_size'] != engine.N:
+        raise ValueError('checkpoint is for dims %r / population %r' % (blob['dims'], blob['pop_size']))
+    engine.theta.copy_(torch.from_numpy(blob['theta']))
+    engine.adam_m.copy_(torch.from_numpy(blob['adam_m']))
+    engine.adam_v.copy_(torch.from_numpy(blob['adam_v']))
+    s = blob['state']
+    raw = bytes(State(s['generation'], s['adam_t'], s['beta1_t'], s['beta2_t']))
+    engine.state.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+    engine.seed = blob['seed']
+    engine.generation_index = int(s['generation'])
+    if engine.normalize_obs and blob['obs_stats'] is not None:
+        engine.obs_stats.copy_(torch.from_numpy(blob['obs_stats']))
