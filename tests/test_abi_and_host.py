@@ -160,3 +160,23 @@ def test_product_never_touches_the_oracle():
     bench = open(os.path.join(REPO, 'bench.py')).read()
     ours = bench.split('def run_ours')[1].split("if __name__ == '__main__'")[0]
     assert not re.search(r'^\s*(from|import)\s+oracle', ours, re.M)      # only the cpu subprocess leg uses it
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours): one JSON line with the contract's keys."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(REPO, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0',
+                        '--pop', '256', '--hidden', '64', '--tape-len', '128', '--cpu-sample', '32'],
+                       capture_output=True, text=True, timeout=300, cwd=REPO)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1                                     # exactly one line on stdout
+    d = json.loads(lines[0])
+    for key in ['impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e']:
+        assert key in d, key
+    assert d['impl'] == 'reference' and d['metric'] == 'nes_policy_evals_per_sec' and d['higher_is_better'] is True
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['value'] > 0
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert 'workload' in d['config']
