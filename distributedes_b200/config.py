@@ -6,14 +6,15 @@ from __future__ import annotations
 
 import numpy as np
 
-from .envs import TapeEnv
+from .envs import DeviceEnv, TapeEnv
 from .model import StandardFCNet
 from .utils import Adam
 
 
 class BasicConfig:
     def __init__(self, hidden_size):
-        self.env_fn = lambda: TapeEnv(self.state_dim_, self.action_dim_, self.tape_len)
+        if not hasattr(self, 'env_fn'):
+            self.env_fn = lambda: TapeEnv(self.state_dim_, self.action_dim_, self.tape_len)
         self.repetitions = 1          # the tape is deterministic: one episode per evaluation (reference: 10)
         self.test_repetitions = 1
         env = self.env_fn()
@@ -54,6 +55,24 @@ class PendulumConfig(SynthTapeConfig):
 
     def __init__(self, hidden_size=16, tape_len=200):
         SynthTapeConfig.__init__(self, hidden_size, 3, 1, tape_len, 2.0)
+
+
+class ClosedLoopPendulumConfig(BasicConfig):
+    """The reference's PendulumConfig (config.py:26-31) with the environment stepped on the device: 10 repetitions of
+    200-step episodes per member (config.py:8-9), per-member observations, observation normaliser on."""
+
+    def __init__(self, hidden_size=64):
+        self.task = 'Pendulum-v0'
+        self.clip = 2.0
+        self.action_clip = lambda a: np.clip(a, -2, 2)
+        self.target = 10000
+        self.tape_len = DeviceEnv.SPECS[self.task]['horizon']
+        self.env_fn = lambda: DeviceEnv(self.task)
+        BasicConfig.__init__(self, hidden_size)
+        self.closed_loop = True
+        self.repetitions = 10         # config.py:8
+        self.test_repetitions = 10    # config.py:9
+        self.normalize_obs = True
 
 
 class BipedalWalkerConfig(SynthTapeConfig):

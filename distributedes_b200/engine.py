@@ -73,9 +73,7 @@ class NESEngine:
         self.normalize_obs = bool(normalize_obs)
         self.repetitions = int(repetitions)
         self.obs_stats = torch.zeros(2 * self.d0 + 1, dtype=torch.float32, device=dev) if self.normalize_obs else None
-        self.set_tape(obs, target)
-        self.eval_ws = (self.k.eval_workspace(self.d0, self.H, self.A, self.T, precision, dev)
-                        if hasattr(self.k, 'eval_workspace') else None)
+        self._setup_inputs(obs, target)
         self.generation_index = 0
         self._graph = None
         # single GPU: the whole generation is one CUDA graph.  With a process group the generation stays eager
@@ -85,6 +83,11 @@ class NESEngine:
                            and (self.world == 1 or os.environ.get('DES_GRAPH_NCCL') == '1'))
 
     # -- inputs ------------------------------------------------------------------------------------------
+    def _setup_inputs(self, obs, target):
+        self.set_tape(obs, target)
+        self.eval_ws = (self.k.eval_workspace(self.d0, self.H, self.A, self.T, self.precision, self.device)
+                        if hasattr(self.k, 'eval_workspace') else None)
+
     def set_tape(self, obs, target):
         obs = torch.as_tensor(obs, dtype=torch.float32)
         target = torch.as_tensor(target, dtype=torch.float32)
@@ -131,6 +134,9 @@ class NESEngine:
                          learning_rate=self.lr, weight_decay=self.wd, beta1=self.beta1, beta2=self.beta2,
                          epsilon=self.epsilon, update_out=self.update)
         self.k.state_advance(self.state, self.beta1, self.beta2)
+        self._merge_obs_stats()
+
+    def _merge_obs_stats(self):
         if self.normalize_obs:
             # natural_es.py:85-89: merge this generation's online statistics (every member saw the whole tape;
             # all ranks hold identical online stats, so the merged result needs no collective)
@@ -203,3 +209,85 @@ class NESEngine:
 
     def theta_numpy(self):
         return self.theta.detach().cpu().numpy()
+
+
+class RolloutEngine(NESEngine):
+    """NES generation whose fitness comes from closed-loop episodes stepped on the device: the
+    reference's real workload — Evaluator.eval utils.py:116-124 runs `repetitions` episodes of the environment per
+    member, every member seeing its own observations.  Environment: 'Pendulum-v0' (config.py:26-31).
+
+    Differences from the tape engine: `evaluate` calls des_rollout_eval; the observation statistics are those of the
+    states actually visited, so each rank contributes fp64 (sum, sum of squares, count) of its members' observations
+    and one (2*d0+1)-double all-reduce replaces the per-worker Chan merges of natural_es.py:85-89."""
+
+    ENVS = {'Pendulum-v0': dict(env=0, state_dim=3, action_dim=1, clip=2.0, horizon=200)}
+
+    def __init__(self, *, task='Pendulum-v0', hidden, pop_size, theta0, sigma, learning_rate, repetitions=10,
+                 horizon=None, action_noise_std=0.0, normalize_obs=True, **kw):
+        if task not in self.ENVS:
+            raise ValueError('closed-loop environments available on the device: %s (got %r)' % (sorted(self.ENVS), task))
+        e = self.ENVS[task]
+        self.env_id, self.horizon = e['env'], int(horizon or e['horizon'])
+        self.action_noise_std = float(action_noise_std)
+        kw.setdefault('clip', e['clip'])
+        kw.pop('precision', None)
+        super().__init__(state_dim=e['state_dim'], hidden=hidden, action_dim=e['action_dim'], pop_size=pop_size,
+                         theta0=theta0, obs=None, target=None, sigma=sigma, learning_rate=learning_rate,
+                         precision='fp32', normalize_obs=normalize_obs, repetitions=repetitions, **kw)
+
+    def _setup_inputs(self, obs, target):
+        self.T = self.horizon
+        self.eval_ws = None
+        w = 2 * self.d0 + 1
+        self.obs_totals = torch.zeros(w, dtype=torch.float64, device=self.device)
+        self.roll_ws = torch.empty(max(self.n_local, 1) * w, dtype=torch.float64, device=self.device)
+
+    def set_tape(self, obs, target):
+        raise TypeError('RolloutEngine steps the environment on the device; there is no tape to set')
+
+    def evaluate(self):
+        if self.world > 1:
+            self.fitness_all.zero_()
+        self.obs_totals.zero_()
+        if self.n_local:
+            self.k.rollout_eval(self.theta, env=self.env_id, hidden=self.H, horizon=self.horizon,
+                                repetitions=self.repetitions, sigma=self.sigma, clip=self.clip,
+                                action_noise_std=self.action_noise_std, seed=self.seed, state=self.state,
+                                member_offset=self.offset, n_local=self.n_local,
+                                obs_stats=self.obs_stats if self.normalize_obs else None,
+                                totals_out=self.obs_totals if self.normalize_obs else None, workspace=self.roll_ws,
+                                out=self.fitness_all[self.offset:self.offset + self.n_local])
+        if self.world > 1:
+            dist.all_reduce(self.fitness_all, group=self.pg)
+            if self.normalize_obs:
+                dist.all_reduce(self.obs_totals, group=self.pg)
+        return self.fitness_all
+
+    def _merge_obs_stats(self):
+        if self.normalize_obs:
+            self.k.obs_stats_merge_totals(self.obs_stats, self.obs_totals, self.d0)
+
+    def generation_host(self, theta_out_host=None, fitness_out_host=None):
+        """generation -> D2H (theta, fitness); a closed-loop generation has no per-step host input."""
+        self.generation()
+        if theta_out_host is not None:
+            theta_out_host.copy_(self.theta, non_blocking=True)
+        if fitness_out_host is not None:
+            fitness_out_host.copy_(self.fitness_all, non_blocking=True)
+        if self.device.type == 'cuda':
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def test_returns(self, solution=None, repetitions=None):
+        """Returns of `repetitions` test episodes of the unperturbed solution (test(), natural_es.py:101-110)."""
+        theta = self.theta if solution is None else torch.as_tensor(
+            np.ascontiguousarray(solution, dtype=np.float32)).to(self.device)
+        reps = int(repetitions or self.repetitions)
+        episodes = torch.empty(reps, dtype=torch.float32, device=self.device)
+        self.k.rollout_eval(theta, env=self.env_id, hidden=self.H, horizon=self.horizon, repetitions=reps,
+                            sigma=0.0, clip=self.clip, action_noise_std=self.action_noise_std, seed=self.seed,
+                            state=self.state, member_offset=0, n_local=1, noiseless=True,
+                            obs_stats=self.obs_stats if self.normalize_obs else None, episodes_out=episodes)
+        return episodes.cpu().numpy().astype(np.float64)
+
+    def noiseless_fitness(self, solution=None):
+        return float(self.test_returns(solution).mean())

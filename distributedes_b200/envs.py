@@ -23,3 +23,23 @@ class TapeEnv:
         self.observation_space = _Box((state_dim,))
         self.action_space = _Box((action_dim,))
         self.tape_len = int(tape_len)
+
+
+class DeviceEnv:
+    """Shape descriptor of an environment that is stepped INSIDE des_rollout_eval (closed loop, per-member
+    observations): there is no host-side step().  'Pendulum-v0': config.py:26-31."""
+    SPECS = {'Pendulum-v0': dict(state_dim=3, action_dim=1, horizon=200, clip=2.0)}
+
+    def __init__(self, task):
+        if task not in self.SPECS:
+            raise ValueError('no device environment %r (available: %s)' % (task, sorted(self.SPECS)))
+        spec = self.SPECS[task]
+        self.task = task
+        self.observation_space = _Box((spec['state_dim'],))
+        self.action_space = _Box((spec['action_dim'],))
+        self.horizon, self.clip = spec['horizon'], spec['clip']
+
+    def reset(self):
+        raise RuntimeError('%s is stepped on the GPU by des_rollout_eval; it has no host-side reset/step' % self.task)
+
+    step = reset

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .engine import NESEngine
+from .engine import NESEngine, RolloutEngine
 from .utils import Evaluator, SharedStats, StaticNormalizer, logger
 
 
@@ -43,6 +43,13 @@ class Worker:
 def build_engine(config, param=None, **kw):
     env = config.env_fn()
     theta0 = config.initial_weight if param is None else np.asarray(param, dtype=np.float32)
+    if getattr(config, 'closed_loop', False):         # environment stepped on the device
+        return RolloutEngine(task=config.task, hidden=config.hidden_size, pop_size=config.pop_size, theta0=theta0,
+                             sigma=config.sigma, learning_rate=config.learning_rate, weight_decay=config.weight_decay,
+                             clip=config.clip, seed=getattr(config, 'seed', 0), beta1=config.opt.beta1,
+                             beta2=config.opt.beta2, epsilon=config.opt.epsilon, repetitions=config.repetitions,
+                             action_noise_std=config.action_noise_std,
+                             normalize_obs=getattr(config, 'normalize_obs', True), **kw)
     return NESEngine(state_dim=config.state_dim, hidden=config.hidden_size, action_dim=config.action_dim,
                      pop_size=config.pop_size, theta0=theta0, obs=env.obs, target=env.target, sigma=config.sigma,
                      learning_rate=config.learning_rate, weight_decay=config.weight_decay, clip=config.clip,
@@ -92,7 +99,9 @@ def train(config, engine=None):
 def test(config, solution, stats, engine=None):
     """natural_es.py:101-110: mean and 'ste' of test_repetitions noiseless episodes of `solution`
     (None = the engine's current parameters)."""
-    if engine is not None:
+    if engine is not None and hasattr(engine, 'test_returns'):      # closed loop: distinct reset states per episode
+        rewards = engine.test_returns(solution, config.test_repetitions)
+    elif engine is not None:
         rewards = [engine.noiseless_fitness(solution) for _ in range(config.test_repetitions)]
     else:
         normalizer = StaticNormalizer(config.state_dim)

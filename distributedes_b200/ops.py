@@ -116,6 +116,43 @@ def obs_normalize(obs, stats, out=None):
     return out
 
 
+ENV_DIMS = {0: (3, 1)}      # DES_ENV_PENDULUM: (state_dim, action_dim)
+
+
+def rollout_eval(theta, *, env=0, hidden, horizon=200, repetitions=10, sigma, clip, action_noise_std=0.0, seed,
+                 generation=0, state=None, member_offset=0, n_local, noiseless=False, obs_stats=None, totals_out=None,
+                 workspace=None, out=None, episodes_out=None):
+    """Closed-loop fitness of members [member_offset, member_offset + n_local): mean return over `repetitions`
+    episodes stepped on the device (Evaluator.eval utils.py:116-124 over single_run utils.py:126-139)."""
+    if env not in ENV_DIMS:
+        raise RuntimeError('unknown environment id %r' % (env,))
+    d0, A = ENV_DIMS[env]
+    if out is None:
+        out = torch.empty(n_local, dtype=torch.float32, device=theta.device)
+    if totals_out is not None and workspace is None:
+        workspace = torch.empty(max(n_local, 1) * (2 * d0 + 1), dtype=torch.float64, device=theta.device)
+    ws_bytes = workspace.numel() * workspace.element_size() if workspace is not None else 0
+    with _on(theta, 'theta'):
+        _lib.check(_lib.load().des_rollout_eval(
+            _ptr(out, torch.float32, 'out'), _ptr(episodes_out, torch.float32, 'episodes_out', True),
+            _ptr(totals_out, torch.float64, 'totals_out', True), _ptr(theta, torch.float32, 'theta'),
+            _ptr(obs_stats, torch.float32, 'obs_stats', True), int(env), Dims(d0, hidden, A, horizon), int(repetitions),
+            float(sigma), float(clip), float(action_noise_std), int(seed), int(generation),
+            _ptr(state, torch.uint8, 'state', True), int(member_offset), int(n_local), 1 if noiseless else 0,
+            C.c_void_p(workspace.data_ptr()) if workspace is not None else C.c_void_p(0), ws_bytes, _stream()),
+            'des_rollout_eval')
+    return out
+
+
+def obs_stats_merge_totals(stats, totals, state_dim):
+    """Chan merge of a batch given by fp64 [sum | sum of squares | count] into stats [m|v|n] (utils.py:85-96)."""
+    with _on(stats, 'stats'):
+        _lib.check(_lib.load().des_obs_stats_merge_totals(_ptr(stats, torch.float32, 'stats'),
+                                                          _ptr(totals, torch.float64, 'totals'), int(state_dim), _stream()),
+                   'des_obs_stats_merge_totals')
+    return stats
+
+
 def eval_workspace(state_dim, hidden, action_dim, tape_len, precision, device):
     """Optional scratch for des_nes_eval (multi-pass tensor-core shapes); None when the shape needs none."""
     with torch.cuda.device(device):

@@ -118,6 +118,33 @@ DES_API int des_obs_stats_merge(float *stats_dev, const float *obs_dev, int32_t 
 DES_API int des_obs_normalize(float *obs_out_dev, const float *obs_dev, const float *stats_dev, int32_t tape_len,
                       int32_t state_dim, void *stream);
 
+/* ---- closed-loop rollouts: environment stepped on the device ------------------------------- */
+
+#define DES_ENV_PENDULUM 0 /* 'Pendulum-v0' of PendulumConfig config.py:26-31: state_dim 3, action_dim 1, clip 2, 200 steps */
+
+/* fitness_out_dev[i] (i < n_local) = mean over `repetitions` episodes of sum_t reward_t for the policy
+ * theta + sigma*eps_m, m = member_offset + i, each episode stepped in closed loop for dims.tape_len steps:
+ * Worker.run natural_es.py:27-32 -> Evaluator.eval utils.py:116-124 -> single_run utils.py:126-139 (normalise the
+ * observation with obs_stats_dev [m|v|n] or pass it through while n == 0 / NULL, forward, + action_noise_std * N(0,1),
+ * clip, env.step).  Episode (m, r) of generation g resets from counter stream 2: Philox(r, m, g, 2) (see
+ * oracle/pendulum_oracle.py); noiseless != 0 evaluates theta itself over `repetitions` test episodes
+ * (test() natural_es.py:101-110; n_local must be 1, reset member 0x40000000).
+ * episode_returns_out_dev (optional, [n_local][repetitions]) receives the individual episode returns.
+ * obs_totals_out_dev (optional, fp64 [2*state_dim + 1]) receives sum, sum of squares and count of the RAW observations
+ * fed to the normaliser by these members — what the workers' online stats hold (utils.py:68-73) — to be summed over
+ * ranks and merged with des_obs_stats_merge_totals; it needs workspace_dev of n_local * (2*state_dim+1) * 8 bytes.
+ * hidden must be a multiple of 32 (<= 128), repetitions <= 10.  Arithmetic: policy in fp32 (FFMA, accurate tanh),
+ * dynamics in fp64 like gym's float64 state. */
+DES_API int des_rollout_eval(float *fitness_out_dev, float *episode_returns_out_dev, double *obs_totals_out_dev,
+                             const float *theta_dev, const float *obs_stats_dev, int env, des_dims dims, int32_t repetitions, double sigma,
+                             double clip, double action_noise_std, uint64_t seed, uint64_t generation,
+                             const des_state *state_dev, int64_t member_offset, int64_t n_local, int noiseless,
+                             void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* Chan merge (utils.py:85-96) of a batch given by obs_totals_dev = [sum (d0) | sum of squares (d0) | count] into
+ * stats_dev [m|v|n]  (natural_es.py:85-89 after the cross-rank sum of the totals). */
+DES_API int des_obs_stats_merge_totals(float *stats_dev, const double *obs_totals_dev, int32_t state_dim, void *stream);
+
 /* ---- fused sample + forward + fitness ------------------------------------------------------ */
 
 /* fitness_out_dev[i] (i < n_local) = sum_t -|| clip(pi_{theta+sigma*eps_m}(obs_t), -clip, clip) - target_t ||^2

@@ -12,6 +12,8 @@ What comes from where:
   * StandardFCNet forward / flat codec   -> /root/reference/model.py:7-39, called directly
   * per-member fitness                   -> /root/reference/utils.py:108-139 Evaluator.eval over the
                                             stub gym tape env (oracle/gym_stub)
+  * closed-loop Pendulum generations     -> natural_es.train() VERBATIM on the reference's PendulumConfig over the stub
+                                            gym's restated Pendulum-v0 (golden_train_closed), normaliser on
   * one..three full generations          -> /root/reference/natural_es.py:34-99 train() run VERBATIM
                                             (1 worker; np.random.randn replaced by the Philox noise so
                                             member identity is reproducible; config.opt replaced by a
@@ -191,6 +193,74 @@ def golden_train_verbatim(tag, d0, H, A, T, clip, N, seed, sigma, lr, gens, norm
              test_rewards=np.asarray(rewards, dtype=np.float64), train_steps=np.asarray(steps))
 
 
+def golden_train_closed(tag, H, N, reps, seed, sigma, lr, gens):
+    """natural_es.train() verbatim on the reference's own PendulumConfig (config.py:26-31) over the stub gym's restated
+    Pendulum-v0, observation normaliser ON (the reference's real workload).  Hooks: Philox noise for np.random.randn
+    (as above), recording Adam, and the stub's reset hook so episode k of the single worker starts from the counter-RNG
+    state of (generation, member, repetition) and the master's test() episodes from the test stream."""
+    import gym
+    from oracle import pendulum_oracle as po
+    torch.manual_seed(0)
+    first = gym._pendulum_instances[0]            # instance numbers: first = config probe, +1 = worker, +2+g = test(g)
+    cfg = ref_config.PendulumConfig(hidden_size=H)
+    cfg.repetitions = reps
+    cfg.test_repetitions = reps
+    cfg.num_workers = 1
+    cfg.pop_size = N
+    cfg.sigma = sigma
+    cfg.learning_rate = lr
+    cfg.opt = RecordingAdam()
+    cfg.max_steps = (gens + 1) * N * reps * po.HORIZON - 1
+    P = len(cfg.initial_weight)
+    theta0 = cfg.initial_weight.astype(np.float32)
+    counter = {'k': 0}
+    real_randn = np.random.randn
+
+    def philox_randn(*shape):
+        n = shape[0]
+        if n == P:
+            g, member = divmod(counter['k'], N)
+            counter['k'] += 1
+            return orc.noise(seed, g, member, 1, P)[0]
+        return np.zeros(n)
+
+    def reset_hook(instance, episode):
+        if instance == first + 1:                                        # the worker's environment
+            g, rest = divmod(episode, N * reps)
+            member, rep = divmod(rest, reps)
+        else:                                                            # a test() environment
+            g, member, rep = instance - (first + 2), po.TEST_MEMBER, episode
+        th, thd = po.reset_states(seed, g, [member], reps)
+        return th[0, rep], thd[0, rep]
+
+    stats_log = []
+    real_merge = ref_utils.SharedStats.merge
+
+    def logging_merge(self, B):
+        real_merge(self, B)
+        stats_log.append(np.concatenate([self.m.numpy(), self.v.numpy(), self.n.numpy()]).copy())
+
+    np.random.randn = philox_randn
+    gym.pendulum_reset_hook = reset_hook
+    ref_utils.SharedStats.merge = logging_merge
+    try:
+        rewards, steps, _ = ref_nes.train(cfg)
+    finally:
+        np.random.randn = real_randn
+        gym.pendulum_reset_hook = None
+        ref_utils.SharedStats.merge = real_merge
+    assert len(cfg.opt.rec_g) == gens
+    param = torch.FloatTensor(torch.from_numpy(theta0.copy()))
+    thetas = []
+    for st in cfg.opt.rec_step:
+        param.add_(cfg.learning_rate * torch.FloatTensor(st))
+        thetas.append(param.numpy().copy())
+    np.savez(os.path.join(OUT, 'train_closed_%s.npz' % tag), H=H, N=N, reps=reps, seed=seed, sigma=sigma, lr=lr,
+             wd=cfg.weight_decay, gens=gens, theta0=theta0, grad_after_wd=np.stack(cfg.opt.rec_g),
+             adam_step=np.stack(cfg.opt.rec_step), theta=np.stack(thetas), stats=np.stack(stats_log),
+             test_rewards=np.asarray(rewards, dtype=np.float64), train_steps=np.asarray(steps))
+
+
 if __name__ == '__main__':
     golden_fitness_shift()
     golden_adam()
@@ -202,5 +272,7 @@ if __name__ == '__main__':
     # the same with the reference's observation normaliser left ON (SharedStats.merge untouched)
     golden_train_verbatim('pend', 3, 64, 1, 32, 2.0, 16, seed=5, sigma=0.1, lr=0.1, gens=3, normalizer=True)
     golden_train_verbatim('b64', 24, 64, 4, 16, 1.0, 24, seed=6, sigma=0.1, lr=0.1, gens=3, normalizer=True)
+    # BASELINE configs[0]: Pendulum-v0, 2x64 MLP, population 16, 10 repetitions of 200 steps, closed loop
+    golden_train_closed('pend', 64, 16, 10, seed=7, sigma=0.1, lr=0.1, gens=2)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -95,3 +95,34 @@ def obs_stats_merge(stats, obs, n_feed):
     st.merge_tape(obs.numpy(), n_feed)
     stats.copy_(torch.from_numpy(np.concatenate([st.m, st.v, [st.n]]).astype(np.float32)))
     return stats
+
+
+def rollout_eval(theta, *, env=0, hidden, horizon=200, repetitions=10, sigma, clip, action_noise_std=0.0, seed,
+                 generation=0, state=None, member_offset=0, n_local, noiseless=False, obs_stats=None, totals_out=None,
+                 workspace=None, out=None, episodes_out=None):
+    from oracle import pendulum_oracle as po
+    gen = int(state[0]) if state is not None else generation
+    stats = None
+    if obs_stats is not None:
+        a = obs_stats.numpy()
+        stats = (a[:3], a[3:6], a[6])
+    if noiseless:
+        ret = po.test_returns(theta.numpy(), hidden, seed, gen, repetitions, stats, horizon, clip)
+        if episodes_out is not None:
+            episodes_out.copy_(torch.from_numpy(ret.astype(np.float32)))
+        return None
+    fit, (osum, osq, cnt) = po.closed_fitness(theta.numpy(), hidden, sigma, seed, gen, member_offset, n_local,
+                                              repetitions, stats, horizon, clip)
+    out.copy_(torch.from_numpy(fit.astype(np.float32)))
+    if totals_out is not None:
+        totals_out.copy_(torch.from_numpy(np.concatenate([osum, osq, [cnt]])))
+    return out
+
+
+def obs_stats_merge_totals(stats, totals, state_dim):
+    from oracle import pendulum_oracle as po
+    a, t = stats.numpy(), totals.numpy()
+    d0 = state_dim
+    m, v, n = po.merge_totals((a[:d0], a[d0:2 * d0], a[2 * d0]), t[:d0], t[d0:2 * d0], t[2 * d0])
+    stats.copy_(torch.from_numpy(np.concatenate([m, v, [n]]).astype(np.float32)))
+    return stats
