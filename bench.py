@@ -283,6 +283,27 @@ def run_ours(a):
         except Exception as e:
             other = {oprec: {'error': str(e)[:200]}}
 
+    # ---- closed-loop rollouts, for context: Pendulum-v0 stepped on the device, 10 episodes of 200
+    # steps per member, observation normaliser on.  Not the headline; single GPU only.
+    closed = None
+    if world == 1 and not a.no_other_modes:
+        try:
+            from distributedes_b200.engine import RolloutEngine
+            cN, cH = min(N, 65536), 64
+            ceng = RolloutEngine(hidden=cH, pop_size=cN, theta0=StandardFCNet(3, 1, cH, seed=0).get_weight(), sigma=0.1,
+                                 learning_rate=0.1, seed=0, device=dev)
+            for _ in range(3):
+                ceng.generation()
+            c_ms, _ = timed(ceng.generation, max(3, a.steps // 2))
+            c_ms /= max(3, a.steps // 2)
+            closed = {'workload': 'Pendulum-v0 closed loop: pop %d, 2x%d MLP, 10 episodes x 200 steps per member' % (cN, cH),
+                      'ms_per_step': c_ms, 'env_steps_per_sec': cN * 10 * 200 / (c_ms * 1e-3),
+                      'policy_evals_per_sec': cN / (c_ms * 1e-3),
+                      'fp32_tflops': 2.0 * (3 * cH + cH * cH + cH) * cN * 2000 / (c_ms * 1e-3) / 1e12}
+            del ceng
+        except Exception as e:
+            closed = {'error': str(e)[:200]}
+
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -308,7 +329,7 @@ def run_ours(a):
                        'l2': 'flushed: 256 MiB memset between steps, outside the per-step CUDA events',
                        'parallelism': 'population sharded over %d GPU(s); all-reduce fitness[N] + all-reduce partial[P]' % world},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches_per_step * a.steps,
-            'roofline': roofline, 'cpu_baseline': cpu, 'other_modes': other,
+            'roofline': roofline, 'cpu_baseline': cpu, 'other_modes': other, 'closed_loop': closed,
         }
         EMIT(json.dumps(line))
     if world > 1:

@@ -3,11 +3,10 @@
 // environment stepped on the device.  Environment 0 = Pendulum-v0 (the reference's PendulumConfig, config.py:26-31:
 // obs 3, action 1, clip +-2, 200-step episodes).
 //
-// One CTA per member, one warp per episode (repetition).  The member's perturbed weights theta + sigma*eps are generated
-// once into shared memory (same counter noise as every other kernel); each warp then runs its episode sequentially:
-// lane l owns hidden units l, l+32, ..., the 64x64 layer is a shuffle-broadcast mat-vec, the scalar dynamics are
-// computed redundantly by all lanes in fp64 (gym keeps the state in float64).  Per-step work is ~2*(3H + H*H + H) flop:
-// the kernel is latency/issue bound over N*R independent episodes, not a GEMM.
+// One warp per member steps all of the member's episodes in lockstep (see rollout_pendulum_kernel); the member's
+// perturbed weights theta + sigma*eps are generated once into shared memory with the same counter noise as every other
+// kernel.  Policy arithmetic fp32 (FFMA, MUFU-based tanh), dynamics fp64 (gym keeps its state in float64).
+// Algorithmic work per environment step: 2*(3H + H*H + H) flop; no HBM traffic beyond theta (L2 resident).
 #include "des_common.cuh"
 
 namespace des {
@@ -25,7 +24,7 @@ struct RollArgs {
     const float *obs_stats;            // optional [m | v | n] (StaticNormalizer offline stats), NULL = identity
     const des_state *state;
     Layout L;
-    int reps, horizon, S2;             // S2: padded row stride of W2 in shared memory
+    int reps, horizon;
     float sigma, clip, act_noise;
     PhiloxKey key;
     uint32_t gen;
@@ -38,49 +37,71 @@ __device__ __forceinline__ double unit_open(uint32_t x) { return ((double)(x & 0
 
 // gym Pendulum-v0 (gym/envs/classic_control/pendulum.py): g = 10, m = l = 1, dt = 0.05, max_speed 8, max_torque 2
 struct Pendulum {
-    double th, thdot;
+    double th, thdot, sn, cs;
     __device__ void reset(uint32_t rep, uint32_t member, uint32_t gen, const PhiloxKey &key) {
         const uint4 x = philox4x32_10(rep, member, gen, kStreamEnvReset, key);
         th = (2.0 * unit_open(x.x) - 1.0) * 3.141592653589793;        // uniform(-pi, pi)
         thdot = (2.0 * unit_open(x.y) - 1.0) * 1.0;                     // uniform(-1, 1)
     }
-    __device__ void observe(float *o) const {
-        o[0] = (float)cos(th);
-        o[1] = (float)sin(th);
+    // One fp64 sincos per step serves the observation and the torque term: sin(th + pi) = -sin(th).
+    __device__ void observe(float *o) {
+        sincos(th, &sn, &cs);
+        o[0] = (float)cs;
+        o[1] = (float)sn;
         o[2] = (float)thdot;
     }
-    __device__ double step(double u) {                                  // returns the reward
+    __device__ double step(double u) {                                  // returns the reward; observe() came first
         u = fmin(fmax(u, -2.0), 2.0);
-        const double two_pi = 6.283185307179586;
-        double an = fmod(th + 3.141592653589793, two_pi);               // python %: result has the sign of the divisor
-        if (an < 0) an += two_pi;
-        an -= 3.141592653589793;
+        const double two_pi = 6.283185307179586, pi = 3.141592653589793;
+        const double x = th + pi;
+        const double an = (x - two_pi * floor(x * (1.0 / two_pi))) - pi;  // ((th + pi) % 2 pi) - pi, python sign rule
         const double cost = an * an + 0.1 * thdot * thdot + 0.001 * u * u;
-        double nthdot = thdot + (-3.0 * 10.0 / 2.0 * sin(th + 3.141592653589793) + 3.0 * u) * 0.05;
+        const double nthdot = thdot + (15.0 * sn + 3.0 * u) * 0.05;      // -3g/(2l) sin(th + pi) + 3/(m l^2) u
         th = th + nthdot * 0.05;
         thdot = fmin(fmax(nthdot, -8.0), 8.0);
         return -cost;
     }
 };
 
-template <int HPL>   // hidden units per lane (H = 32*HPL)
-__global__ void __launch_bounds__(320) rollout_pendulum_kernel(RollArgs a) {
+// tanh as 1 - 2/(1 + 2^(2x log2 e)): two MUFU + three FP32 ops, abs error ~2e-7 (fp32 rounding level of the
+// reference's torch.tanh).  40*H/32 of these per member-step make the libm tanhf a third of the instruction count.
+__device__ __forceinline__ float tanh_mufu(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return __fmaf_rn(-2.0f, r, 1.0f);
+}
+
+constexpr int kEpPerLane = 5;          // episodes per lane half: 2 halves x 5 = up to 10 repetitions (config.py:8)
+constexpr int kHS = 8;                 // row stride of an h1 panel (one panel per episode half): 5 episodes + pad
+
+// One warp (= one CTA) per member; the warp steps all `reps` episodes of its member in lockstep, so the hidden layer is
+// a [H x H] x [H x reps] product per step instead of `reps` mat-vecs: lane (rg = lane>>1, eg = lane&1) owns the
+// R = H/16 hidden units rg*R.. and the episodes 5*eg..5*eg+4 — an R x 5 register tile fed per k by one LDS of R
+// transposed weights and one 5-float broadcast of h1.  The fp64 dynamics of episode 5*eg + rg%5 run in every lane
+// (the copies in rg >= 5 are redundant), i.e. once per step for the whole member.
+template <int HPL>   // H = 32*HPL
+__global__ void __launch_bounds__(32) rollout_pendulum_kernel(RollArgs a) {
+    constexpr int H = 32 * HPL, R = 2 * HPL, C = kEpPerLane;
     extern __shared__ __align__(16) float sm[];
+    float *W2T = sm;                     // [k][j] = W2[j][k]
+    // h1 panels, one per episode half, rows in the permuted order p(k) = (k % R)*16 + k/R so that the 16 unit groups
+    // storing their r-th unit hit consecutive 32-byte rows; the second panel is shifted by 16 bytes: conflict-free STS.128
+    float *hT = W2T + H * H;             // [2][p(k)][kHS] (+4 floats)
+    float *xs = hT + 2 * H * kHS + 8;    // [10][4] normalised observations
+    float *W1s = xs + 40;                // [H][4]
+    float *b1s = W1s + H * 4;            // [H]
+    float *b2s = b1s + H;
+    float *W3s = b2s + H;
+    float *b3s = W3s + H;                // [4]
+    double *red = reinterpret_cast<double *>(b3s + 4);      // [10][8] per-episode results
     const Layout L = a.L;
-    const int H = L.H, S2 = a.S2;
-    float *W1 = sm;                      // [H][4]  (3 inputs + pad)
-    float *b1 = W1 + H * 4;
-    float *W2 = b1 + H;                  // [H][S2]
-    float *b2 = W2 + H * S2;
-    float *W3 = b2 + H;                  // [H]   (action_dim == 1)
-    float *b3 = W3 + H;                  // [1]
-    __shared__ double ret[16];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x, rg = lane >> 1, eg = lane & 1;
     const uint32_t gen = a.state ? (uint32_t)a.state->generation : a.gen;
     const uint32_t member = (uint32_t)(a.member_offset + blockIdx.x);
 
     // ---- theta' = theta + sigma*eps for this member -> shared memory (natural_es.py:28-30)
-    for (int q = threadIdx.x; q < (L.P + 3) / 4; q += blockDim.x) {
+    for (int q = lane; q < (L.P + 3) / 4; q += 32) {
         float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!a.noiseless) z = noise_quad((uint32_t)q, member, gen, kStreamNesEps, a.key);
         const float zz[4] = {z.x, z.y, z.z, z.w};
@@ -89,15 +110,23 @@ __global__ void __launch_bounds__(320) rollout_pendulum_kernel(RollArgs a) {
             const int j = 4 * q + e;
             if (j >= L.P) break;
             const float w = __fmaf_rn(a.sigma, zz[e], __ldg(a.theta + j));
-            if (j < L.off_b1) W1[(j / 3) * 4 + (j % 3)] = w;
-            else if (j < L.off_w2) b1[j - L.off_b1] = w;
-            else if (j < L.off_b2) { const int r = (j - L.off_w2) / H; W2[r * S2 + (j - L.off_w2 - r * H)] = w; }
-            else if (j < L.off_w3) b2[j - L.off_b2] = w;
-            else if (j < L.off_b3) W3[j - L.off_w3] = w;
-            else b3[0] = w;
+            if (j < L.off_b1) W1s[(j / 3) * 4 + (j % 3)] = w;
+            else if (j < L.off_w2) b1s[j - L.off_b1] = w;
+            else if (j < L.off_b2) { const int r = (j - L.off_w2) / H; const int k = j - L.off_w2 - r * H; W2T[((k % R) * 16 + k / R) * H + r] = w; }
+            else if (j < L.off_w3) b2s[j - L.off_b2] = w;
+            else if (j < L.off_b3) W3s[j - L.off_w3] = w;
+            else b3s[0] = w;
         }
     }
-    __syncthreads();
+    __syncwarp();
+    float w1[R][3], b1[R], b2[R], w3[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int j = rg * R + r;
+        w1[r][0] = W1s[j * 4]; w1[r][1] = W1s[j * 4 + 1]; w1[r][2] = W1s[j * 4 + 2];
+        b1[r] = b1s[j]; b2[r] = b2s[j]; w3[r] = W3s[j];
+    }
+    const float b3 = b3s[0];
 
     // StaticNormalizer (utils.py:48-51): identity while n == 0
     float nm[3] = {0.f, 0.f, 0.f}, ns[3] = {1.f, 1.f, 1.f};
@@ -105,76 +134,118 @@ __global__ void __launch_bounds__(320) rollout_pendulum_kernel(RollArgs a) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) { nm[k] = a.obs_stats[k]; ns[k] = sqrtf(a.obs_stats[3 + k] + 1e-6f); }
     }
+    float *hp = hT + eg * (H * kHS + 4);                  // this lane's h1 panel
+    const int csel = rg % C, ep = C * eg + csel;         // the episode whose dynamics this lane carries
+    const bool writer = rg < C;                           // one lane per episode publishes
+    Pendulum env;
+    env.reset((uint32_t)ep, a.reset_member_base + (a.noiseless ? 0u : (uint32_t)blockIdx.x), gen, a.key);
     double total = 0.0, osum[3] = {0, 0, 0}, osq[3] = {0, 0, 0};
-    if (warp < a.reps) {
-        Pendulum env;
-        env.reset((uint32_t)warp, a.reset_member_base + (a.noiseless ? 0u : (uint32_t)blockIdx.x), gen, a.key);
-        for (int t = 0; t < a.horizon; ++t) {
+    for (int t = 0; t < a.horizon; ++t) {
+        {
             float o[3];
             env.observe(o);
 #pragma unroll
             for (int k = 0; k < 3; ++k) { osum[k] += (double)o[k]; osq[k] += (double)o[k] * (double)o[k]; }
-            float x[3];
+            if (writer)
+                *reinterpret_cast<float4 *>(xs + ep * 4) =
+                    make_float4((o[0] - nm[0]) / ns[0], (o[1] - nm[1]) / ns[1], (o[2] - nm[2]) / ns[2], 0.f);
+        }
+        __syncwarp();
+        // layer 1: the lane's R units x 5 episodes -> h1 panel
+        {
+            float4 x[C];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) x[k] = (o[k] - nm[k]) / ns[k];
-            // layer 1: lane owns hidden units lane + 32*i
-            float h1[HPL];
+            for (int c = 0; c < C; ++c) x[c] = *reinterpret_cast<const float4 *>(xs + (C * eg + c) * 4);
 #pragma unroll
-            for (int i = 0; i < HPL; ++i) {
-                const int j = lane + 32 * i;
-                const float4 w = *reinterpret_cast<const float4 *>(W1 + j * 4);
-                h1[i] = tanhf(__fmaf_rn(w.z, x[2], __fmaf_rn(w.y, x[1], __fmaf_rn(w.x, x[0], b1[j]))));
+            for (int r = 0; r < R; ++r) {
+                float v[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    v[c] = tanh_mufu(__fmaf_rn(w1[r][2], x[c].z, __fmaf_rn(w1[r][1], x[c].y, __fmaf_rn(w1[r][0], x[c].x, b1[r]))));
+                float *dst = hp + (r * 16 + rg) * kHS;
+                *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                dst[4] = v[4];
             }
-            // layer 2: mat-vec, h1 broadcast by shuffles, W2 rows from shared memory (padded stride: conflict free)
-            float acc[HPL];
+        }
+        __syncwarp();
+        // layer 2: R x 5 register tile
+        float acc[R][C];
 #pragma unroll
-            for (int i = 0; i < HPL; ++i) acc[i] = b2[lane + 32 * i];
+        for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int ki = 0; ki < HPL; ++ki) {
-#pragma unroll 8
-                for (int kl = 0; kl < 32; ++kl) {
-                    const float hk = __shfl_sync(0xffffffffu, h1[ki], kl);
-                    const int k = kl + 32 * ki;
+            for (int c = 0; c < C; ++c) acc[r][c] = b2[r];
+#pragma unroll 16
+        for (int k = 0; k < H; ++k) {
+            float w[R];
+            if constexpr (R % 4 == 0) {
 #pragma unroll
-                    for (int i = 0; i < HPL; ++i) acc[i] = __fmaf_rn(W2[(lane + 32 * i) * S2 + k], hk, acc[i]);
+                for (int r4 = 0; r4 < R / 4; ++r4) {
+                    const float4 ww = *reinterpret_cast<const float4 *>(W2T + k * H + rg * R + 4 * r4);
+                    w[4 * r4] = ww.x; w[4 * r4 + 1] = ww.y; w[4 * r4 + 2] = ww.z; w[4 * r4 + 3] = ww.w;
+                }
+            } else {
+#pragma unroll
+                for (int r2 = 0; r2 < R / 2; ++r2) {
+                    const float2 ww = *reinterpret_cast<const float2 *>(W2T + k * H + rg * R + 2 * r2);
+                    w[2 * r2] = ww.x; w[2 * r2 + 1] = ww.y;
                 }
             }
-            // layer 3 (one action): warp reduction in a fixed order
-            float part = 0.f;
+            const float4 h4 = *reinterpret_cast<const float4 *>(hp + k * kHS);      // k runs in the permuted order
+            const float h5 = hp[k * kHS + 4];
 #pragma unroll
-            for (int i = 0; i < HPL; ++i) part = __fmaf_rn(W3[lane + 32 * i], tanhf(acc[i]), part);
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-            float act = part + b3[0];
-            if (a.act_noise != 0.f) {                                    // utils.py:133
-                const uint4 xr = philox4x32_10((uint32_t)t, member * 16u + (uint32_t)warp, gen, kStreamActNoise, a.key);
-                float z0, z1;
-                box_muller(xr.x, xr.y, z0, z1);
-                act = __fmaf_rn(z0, a.act_noise, act);
+            for (int r = 0; r < R; ++r) {
+                acc[r][0] = __fmaf_rn(w[r], h4.x, acc[r][0]);
+                acc[r][1] = __fmaf_rn(w[r], h4.y, acc[r][1]);
+                acc[r][2] = __fmaf_rn(w[r], h4.z, acc[r][2]);
+                acc[r][3] = __fmaf_rn(w[r], h4.w, acc[r][3]);
+                acc[r][4] = __fmaf_rn(w[r], h5, acc[r][4]);
             }
-            act = fminf(fmaxf(act, -a.clip), a.clip);                    // config.action_clip, utils.py:134
-            total += env.step((double)act);                              // utils.py:135-137
         }
+        // layer 3 (one action per episode): partial over the lane's units, butterfly over the 16 unit groups
+        float p[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float s = 0.f;
+#pragma unroll
+            for (int r = 0; r < R; ++r) s = __fmaf_rn(w3[r], tanh_mufu(acc[r][c]), s);
+            p[c] = s;
+        }
+#pragma unroll
+        for (int off = 2; off < 32; off <<= 1)
+#pragma unroll
+            for (int c = 0; c < C; ++c) p[c] += __shfl_xor_sync(0xffffffffu, p[c], off);
+        float act = p[0];
+#pragma unroll
+        for (int c = 1; c < C; ++c) act = (csel == c) ? p[c] : act;
+        act += b3;
+        if (a.act_noise != 0.f) {                                        // utils.py:133
+            const uint4 xr = philox4x32_10((uint32_t)t, member * 16u + (uint32_t)ep, gen, kStreamActNoise, a.key);
+            float z0, z1;
+            box_muller(xr.x, xr.y, z0, z1);
+            act = __fmaf_rn(z0, a.act_noise, act);
+        }
+        act = fminf(fmaxf(act, -a.clip), a.clip);                        // config.action_clip, utils.py:134
+        total += env.step((double)act);                                  // utils.py:135-137
     }
-    if (lane == 0 && warp < 16) ret[warp] = (warp < a.reps) ? total : 0.0;
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if (writer) {
+        red[ep * 8] = total;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { red[ep * 8 + 1 + k] = osum[k]; red[ep * 8 + 4 + k] = osq[k]; }
+    }
+    __syncwarp();
+    if (lane == 0) {
         double s = 0.0;
-        for (int r = 0; r < a.reps; ++r) s += ret[r];
+        for (int r = 0; r < a.reps; ++r) s += red[r * 8];
         a.fitness[blockIdx.x] = (float)(s / a.reps);                     // -cost of utils.py:124
     }
-    if (a.ep_ret && threadIdx.x < a.reps) a.ep_ret[(int64_t)blockIdx.x * a.reps + threadIdx.x] = (float)ret[threadIdx.x];
-    if (a.stat_part) {      // raw observations seen by this member: per-episode partials combined in a fixed order
-        __shared__ double sp[16][6];
-        if (lane == 0 && warp < 16)
-            for (int k = 0; k < 3; ++k) { sp[warp][k] = (warp < a.reps) ? osum[k] : 0.0; sp[warp][3 + k] = (warp < a.reps) ? osq[k] : 0.0; }
-        __syncthreads();
-        if (threadIdx.x < 6) {
+    if (a.ep_ret && lane < a.reps) a.ep_ret[(int64_t)blockIdx.x * a.reps + lane] = (float)red[lane * 8];
+    if (a.stat_part) {      // raw observations fed to the normaliser by this member, episodes summed in a fixed order
+        if (lane < 6) {
             double s = 0.0;
-            for (int r = 0; r < a.reps; ++r) s += sp[r][threadIdx.x];
-            a.stat_part[(int64_t)blockIdx.x * 7 + threadIdx.x] = s;
+            for (int r = 0; r < a.reps; ++r) s += red[r * 8 + 1 + lane];
+            a.stat_part[(int64_t)blockIdx.x * 7 + lane] = s;
         }
-        if (threadIdx.x == 6) a.stat_part[(int64_t)blockIdx.x * 7 + 6] = (double)a.reps * a.horizon;
+        if (lane == 6) a.stat_part[(int64_t)blockIdx.x * 7 + 6] = (double)a.reps * a.horizon;
     }
 }
 
@@ -231,7 +302,6 @@ extern "C" DES_API int des_rollout_eval(float *fitness_out_dev, float *episode_r
     a.fitness = fitness_out_dev; a.ep_ret = episode_returns_out_dev; a.theta = theta_dev; a.obs_stats = obs_stats_dev; a.state = state_dev;
     a.L = Layout(3, dims.hidden, 1);
     a.reps = repetitions; a.horizon = dims.tape_len;
-    a.S2 = dims.hidden + 1;
     a.sigma = noiseless ? 0.f : (float)sigma; a.clip = (float)clip; a.act_noise = (float)action_noise_std;
     a.key = make_philox_key(seed); a.gen = (uint32_t)generation;
     a.member_offset = (uint64_t)member_offset;
@@ -247,12 +317,12 @@ extern "C" DES_API int des_rollout_eval(float *fitness_out_dev, float *episode_r
         a.stat_part = (double *)workspace_dev;
     }
     const int H = dims.hidden;
-    const size_t smem = sizeof(float) * ((size_t)H * 4 + H + (size_t)H * a.S2 + H + H + 4);
-    const int threads = 32 * repetitions;
+    const size_t smem = sizeof(float) * ((size_t)H * H + 2 * (size_t)H * kHS + 8 + 40 + (size_t)H * 4 + 3 * (size_t)H + 4) +
+                        sizeof(double) * 80;
 #define DES_ROLL_LAUNCH(HPL)                                                                                        \
     do {                                                                                                            \
         DES_CUDA(cudaFuncSetAttribute(rollout_pendulum_kernel<HPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        rollout_pendulum_kernel<HPL><<<(unsigned)n_local, threads, smem, st>>>(a);                                  \
+        rollout_pendulum_kernel<HPL><<<(unsigned)n_local, 32, smem, st>>>(a);                                  \
     } while (0)
     switch (H / 32) {
         case 1: DES_ROLL_LAUNCH(1); break;
