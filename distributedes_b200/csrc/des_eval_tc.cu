@@ -505,12 +505,9 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
         constexpr int kSlotsPerMember = C::NCH + C::NCH * C::KAT;
         uint8_t *const cache = (a.cache && a.n_pass > 1)
                                    ? a.cache + (size_t)blockIdx.x * kSlotsPerMember * C::SLOT_BYTES : nullptr;
-        // theta of this thread's W2 octet is prefetched one ring slot ahead (it does not depend on the member)
         const int r2 = gtid >> 3, c82 = gtid & 7;
         const int row_base = PAIR ? 64 * (int)rank : 0;                  // this CTA's 64 rows of every kNC-row chunk
         auto w2_index = [&](int nc, int ka) { return L.off_w2 + (nc * kNC + row_base + r2) * H + ka * 64 + c82 * 8; };
-        float4 tn0 = __ldg(reinterpret_cast<const float4 *>(a.theta + w2_index(0, 0)));
-        float4 tn1 = __ldg(reinterpret_cast<const float4 *>(a.theta + w2_index(0, 0) + 4));
         for (int64_t m = first; m < a.n_local; m += stride, ++mi) {
             const uint32_t member = (uint32_t)(a.member_offset + (uint64_t)m);
             // ---- small fp32 arrays: b1 | b2 | W3[8][H] | b3[8]
@@ -589,12 +586,11 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
                             mbar_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
                             put_octet<X3>(slot, r2, c82, hi, lo);
                         } else {   // 64 rows x 8 octets = 512 items: one per thread
-                            const float4 t0 = tn0, t1 = tn1;
-                            int nnc = nc, nka = ka + 1;                       // next slot (wraps to the next member)
-                            if (nka == C::KAT) { nka = 0; if (++nnc == C::NCH) nnc = 0; }
-                            tn0 = __ldg(reinterpret_cast<const float4 *>(a.theta + w2_index(nnc, nka)));
-                            tn1 = __ldg(reinterpret_cast<const float4 *>(a.theta + w2_index(nnc, nka) + 4));
+                            // theta is consumed by the last FFMA of perturbed_quad, ~250 instructions after this
+                            // load issues: the L2 latency is covered without carrying a prefetch across the ring wait
                             const int j0 = w2_index(nc, ka);
+                            const float4 t0 = __ldg(reinterpret_cast<const float4 *>(a.theta + j0));
+                            const float4 t1 = __ldg(reinterpret_cast<const float4 *>(a.theta + j0 + 4));
                             const float4 w0 = perturbed_quad((uint32_t)(j0 >> 2), member, gen, kStreamNesEps, a.key,
                                                              a.neg2ln2_sigma2, t0);
                             const float4 w1 = perturbed_quad((uint32_t)(j0 >> 2) + 1, member, gen, kStreamNesEps, a.key,
