@@ -381,15 +381,17 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
                             tc_fence_after();
                         }
                         uint32_t hi[16], lo[16];
-                        if (X3) {
+                        if (X3) {       // b1 holds b * 2log2(e) in this mode (see the generator)
                             const float4 *bq = reinterpret_cast<const float4 *>(b1 + nc * kNC + half * 32);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const float4 b = bq[i];
-                                const float x0 = __uint_as_float(v[4 * i]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
-                                const float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
-                                split_h2(tanh_acc(x0), tanh_acc(x1), hi[2 * i], lo[2 * i]);
-                                split_h2(tanh_acc(x2), tanh_acc(x3), hi[2 * i + 1], lo[2 * i + 1]);
+                                const float2 h01 = tanh_acc2(make_float2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])),
+                                                             make_float2(b.x, b.y));
+                                const float2 h23 = tanh_acc2(make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])),
+                                                             make_float2(b.z, b.w));
+                                split_h2p(h01, hi[2 * i], lo[2 * i]);
+                                split_h2p(h23, hi[2 * i + 1], lo[2 * i + 1]);
                             }
                         } else {
                             // (tanh.approx.f16x2 was tried here: SASS issues one MUFU.TANH.F16 per half plus a PRMT,
@@ -398,10 +400,12 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const float4 b = bq[i];
-                                const float x0 = __uint_as_float(v[4 * i]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
-                                const float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
-                                hi[2 * i] = pack_h2(tanh_fast(x0), tanh_fast(x1));
-                                hi[2 * i + 1] = pack_h2(tanh_fast(x2), tanh_fast(x3));
+                                const float2 x01 = fadd2(make_float2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])),
+                                                         make_float2(b.x, b.y));
+                                const float2 x23 = fadd2(make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])),
+                                                         make_float2(b.z, b.w));
+                                hi[2 * i] = pack_h2(tanh_fast(x01.x), tanh_fast(x01.y));
+                                hi[2 * i + 1] = pack_h2(tanh_fast(x23.x), tanh_fast(x23.y));
                             }
                         }
                         tmem_st16(sbase + nc * (kNC / 2) + half * 16, hi);
@@ -437,10 +441,17 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
 #pragma unroll
                         for (int i4 = 0; i4 < 8; ++i4) {
                             const float4 b = bq[i4];
-                            const float x0 = __uint_as_float(v[4 * i4]) + b.x, x1 = __uint_as_float(v[4 * i4 + 1]) + b.y;
-                            const float x2 = __uint_as_float(v[4 * i4 + 2]) + b.z, x3 = __uint_as_float(v[4 * i4 + 3]) + b.w;
-                            const float2 h01 = X3 ? make_float2(tanh_acc(x0), tanh_acc(x1)) : make_float2(tanh_fast(x0), tanh_fast(x1));
-                            const float2 h23 = X3 ? make_float2(tanh_acc(x2), tanh_acc(x3)) : make_float2(tanh_fast(x2), tanh_fast(x3));
+                            const float2 v01 = make_float2(__uint_as_float(v[4 * i4]), __uint_as_float(v[4 * i4 + 1]));
+                            const float2 v23 = make_float2(__uint_as_float(v[4 * i4 + 2]), __uint_as_float(v[4 * i4 + 3]));
+                            float2 h01, h23;
+                            if (X3) {           // b2 holds b * 2log2(e)
+                                h01 = tanh_acc2(v01, make_float2(b.x, b.y));
+                                h23 = tanh_acc2(v23, make_float2(b.z, b.w));
+                            } else {
+                                const float2 x01 = fadd2(v01, make_float2(b.x, b.y)), x23 = fadd2(v23, make_float2(b.z, b.w));
+                                h01 = make_float2(tanh_fast(x01.x), tanh_fast(x01.y));
+                                h23 = make_float2(tanh_fast(x23.x), tanh_fast(x23.y));
+                            }
                             // layer 3 (model.py:38) in fp32 on packed FFMA2: W3' row-major [q][n], 4 consecutive n per LDS.128
 #pragma unroll
                             for (int q = 0; q < kMaxA; ++q) {
@@ -517,10 +528,13 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
             for (int i = gtid; i < H / 4; i += kGenThreads) {                // b1, b2: aligned quads
                 const float4 v1 = perturbed_quad((uint32_t)((L.off_b1 >> 2) + i), member, gen, kStreamNesEps, a.key,
                                                  a.neg2ln2_sigma2, __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_b1) + i));
-                reinterpret_cast<float4 *>(sm)[i] = v1;
-                reinterpret_cast<float4 *>(sm + H)[i] =
+                const float4 v2 =
                     perturbed_quad((uint32_t)((L.off_b2 >> 2) + i), member, gen, kStreamNesEps, a.key, a.neg2ln2_sigma2,
                                    __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_b2) + i));
+                // f16x3 epilogue evaluates tanh(v + b) as 1 - 2/(1 + 2^(v*c + b*c)), c = 2 log2 e: store b*c
+                const float bsc = X3 ? kTwoLog2e : 1.0f;
+                reinterpret_cast<float4 *>(sm)[i] = make_float4(v1.x * bsc, v1.y * bsc, v1.z * bsc, v1.w * bsc);
+                reinterpret_cast<float4 *>(sm + H)[i] = make_float4(v2.x * bsc, v2.y * bsc, v2.z * bsc, v2.w * bsc);
             }
             for (int i = gtid; i < L.A * H / 4; i += kGenThreads)            // W3' [q][n] row-major: aligned quads
                 reinterpret_cast<float4 *>(sm + 2 * H)[i] =

@@ -189,6 +189,48 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return d;
 }
 
+__device__ __forceinline__ uint64_t pk2(float2 a) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ float2 upk2(uint64_t r) {
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {          // two fp32 adds in one issue slot
+    uint64_t rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(pk2(a)), "l"(pk2(b)));
+    return upk2(rd);
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+    uint64_t rd;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(pk2(a)), "l"(pk2(b)));
+    return upk2(rd);
+}
+// tanh(v + b) for two lanes with the bias pre-scaled: bs = b * 2 log2(e).
+//   e = 2^(v * 2log2e + bs);  tanh = 1 - 2/(1 + e)      abs err ~2e-7; 2 MUFU + 1.5 packed FP32 ops per element
+constexpr float kTwoLog2e = 2.8853900817779268f;
+__device__ __forceinline__ float2 tanh_acc2(float2 v, float2 bs) {
+    const float2 arg = ffma2(v, make_float2(kTwoLog2e, kTwoLog2e), bs);
+    float2 e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(arg.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(arg.y));
+    const float2 d = fadd2(e, make_float2(1.0f, 1.0f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
+    return ffma2(make_float2(-2.0f, -2.0f), r, make_float2(1.0f, 1.0f));
+}
+// hi = fp16(x), lo = fp16(x - hi) for a pair, the subtraction packed
+__device__ __forceinline__ void split_h2p(float2 x, uint32_t &hi, uint32_t &lo) {
+    const __half2 h = __floats2half2_rn(x.x, x.y);
+    const float2 d = fsub2(x, __half22float2(h));
+    const __half2 l = __floats2half2_rn(d.x, d.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
 __device__ __forceinline__ float tanh_fast(float x) {       // MUFU.TANH, max rel err 2^-11
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
