@@ -150,6 +150,8 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+constexpr int kThetaStageBytes = 2 * 2 * kGenWarps * 32 * 16;   // two stages x two 16-byte halves per generator thread
+
 template <int H, int MODE, int NT, bool PAIR>
 __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(TcArgs a) {
     static_assert(!PAIR || NT == 1, "a CTA pair keeps one tile per CTA");
@@ -167,6 +169,8 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
     uint8_t *ring = xs + (size_t)a.n_tiles * C::X_TILE_BYTES;                    // n_slots * SLOT_BYTES
     float *small = reinterpret_cast<float *>(ring + (size_t)a.n_slots * C::SLOT_BYTES);   // [2][SMALL_FLOATS]
     TcBars *bars = reinterpret_cast<TcBars *>(small + 2 * C::SMALL_FLOATS);
+    // theta of the NEXT layer-2 slot, staged per generator thread by cp.async: [stage][half][thread] x 16 bytes
+    float4 *th_stage = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(bars + 1) + 15) & ~(uintptr_t)15);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_epi_warps = kEpiWarps;
@@ -519,6 +523,18 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
         const int r2 = gtid >> 3, c82 = gtid & 7;
         const int row_base = PAIR ? 64 * (int)rank : 0;                  // this CTA's 64 rows of every kNC-row chunk
         auto w2_index = [&](int nc, int ka) { return L.off_w2 + (nc * kNC + row_base + r2) * H + ka * 64 + c82 * 8; };
+        // theta of a layer-2 octet does not depend on the member: it is copied one slot ahead into this thread's own
+        // staging cells with cp.async (no registers, no scoreboard), so its L2 latency never reaches the FFMAs
+        uint32_t tq = 0;                                                 // generated layer-2 slots so far (stage = tq & 1)
+        auto stage_cell = [&](uint32_t st, int half) { return th_stage + (st * 2 + half) * kGenThreads + gtid; };
+        auto stage_fetch = [&](uint32_t st, int nc, int ka) {
+            const float *src = a.theta + w2_index(nc, ka);
+            cp_async16(smem_u32(stage_cell(st, 0)), src);
+            cp_async16(smem_u32(stage_cell(st, 1)), src + 4);
+            cp_async_commit();
+        };
+        constexpr bool kStageTheta = X3;      // measured: +1 % in f16x3 mode, -1 % in f16 mode (one ring slot fewer)
+        if (kStageTheta) stage_fetch(0, 0, 0);
         for (int64_t m = first; m < a.n_local; m += stride, ++mi) {
             const uint32_t member = (uint32_t)(a.member_offset + (uint64_t)m);
             // ---- small fp32 arrays: b1 | b2 | W3[8][H] | b3[8]
@@ -600,15 +616,32 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
                             mbar_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
                             put_octet<X3>(slot, r2, c82, hi, lo);
                         } else {   // 64 rows x 8 octets = 512 items: one per thread
-                            // theta is consumed by the last FFMA of perturbed_quad, ~250 instructions after this
-                            // load issues: the L2 latency is covered without carrying a prefetch across the ring wait
+                            const uint32_t stg = tq & 1;
+                            ++tq;
+                            int nnc = nc, nka = ka + 1;                       // next generated slot (wraps to the next member)
+                            if (nka == C::KAT) { nka = 0; if (++nnc == C::NCH) nnc = 0; }
+                            if (kStageTheta) stage_fetch(stg ^ 1, nnc, nka);
                             const int j0 = w2_index(nc, ka);
-                            const float4 t0 = __ldg(reinterpret_cast<const float4 *>(a.theta + j0));
-                            const float4 t1 = __ldg(reinterpret_cast<const float4 *>(a.theta + j0 + 4));
-                            const float4 w0 = perturbed_quad((uint32_t)(j0 >> 2), member, gen, kStreamNesEps, a.key,
-                                                             a.neg2ln2_sigma2, t0);
-                            const float4 w1 = perturbed_quad((uint32_t)(j0 >> 2) + 1, member, gen, kStreamNesEps, a.key,
-                                                             a.neg2ln2_sigma2, t1);
+                            float4 t0, t1;
+                            if (!kStageTheta) {
+                                t0 = __ldg(reinterpret_cast<const float4 *>(a.theta + j0));
+                                t1 = __ldg(reinterpret_cast<const float4 *>(a.theta + j0 + 4));
+                            }
+                            const uint4 x0 = philox4x32_10((uint32_t)(j0 >> 2), member, gen, kStreamNesEps, a.key);
+                            const uint4 x1 = philox4x32_10((uint32_t)(j0 >> 2) + 1, member, gen, kStreamNesEps, a.key);
+                            const BmParts pa = box_muller_parts(x0.x, x0.y, a.neg2ln2_sigma2);
+                            const BmParts pb = box_muller_parts(x0.z, x0.w, a.neg2ln2_sigma2);
+                            const BmParts pc = box_muller_parts(x1.x, x1.y, a.neg2ln2_sigma2);
+                            const BmParts pd = box_muller_parts(x1.z, x1.w, a.neg2ln2_sigma2);
+                            if (kStageTheta) {
+                                cp_async_wait<1>();                           // this slot's theta has landed
+                                t0 = *stage_cell(stg, 0);
+                                t1 = *stage_cell(stg, 1);
+                            }
+                            const float4 w0 = make_float4(__fmaf_rn(pa.nr, pa.c, t0.x), __fmaf_rn(pa.nr, pa.s, t0.y),
+                                                          __fmaf_rn(pb.nr, pb.c, t0.z), __fmaf_rn(pb.nr, pb.s, t0.w));
+                            const float4 w1 = make_float4(__fmaf_rn(pc.nr, pc.c, t1.x), __fmaf_rn(pc.nr, pc.s, t1.y),
+                                                          __fmaf_rn(pd.nr, pd.c, t1.z), __fmaf_rn(pd.nr, pd.s, t1.w));
                             const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
                             mbar_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
                             store_octet<X3>(slot, mirror, r2, c82, w);
@@ -621,6 +654,7 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
             }
         }
     }
+    cp_async_wait<0>();                    // the generators' last (unused) theta prefetch
     tc_fence_before();
     __syncthreads();
     if (PAIR) cluster_sync_all();          // no CTA leaves (or frees TMEM) while its peer may still signal or read it
@@ -636,7 +670,7 @@ static int launch_tc_nt(TcArgs &a, cudaStream_t st) {
     const int tiles_total = a.T / 128;
     a.n_pass = tiles_total / (PAIR ? 2 : NT);
     a.n_tiles = PAIR ? a.n_pass : tiles_total;                 // X tiles held by ONE CTA
-    const size_t fixed = 2 * C::SMALL_FLOATS * sizeof(float) + sizeof(TcBars) + 1024;
+    const size_t fixed = 2 * C::SMALL_FLOATS * sizeof(float) + sizeof(TcBars) + 1024 + (C::X3 ? kThetaStageBytes + 16 : 0);
     const size_t xbytes = (size_t)a.n_tiles * C::X_TILE_BYTES;
     const int per_member = C::NCH + C::NCH * C::KAT;
     int n_slots = xbytes + fixed >= 227 * 1024 ? 0 : (int)((227 * 1024 - fixed - xbytes) / C::SLOT_BYTES);

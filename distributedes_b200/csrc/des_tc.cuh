@@ -152,6 +152,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&w)[16
           "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]) : "memory");
 }
 
+// ---- per-thread asynchronous global->shared copies (LDGSTS): no destination registers, no scoreboard held ---------
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- fp16 packing -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {       // element k (even) low half, k+1 high half
     const __half2 h = __floats2half2_rn(lo, hi);
@@ -211,6 +219,9 @@ __device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
 }
 // tanh(v + b) for two lanes with the bias pre-scaled: bs = b * 2 log2(e).
 //   e = 2^(v * 2log2e + bs);  tanh = 1 - 2/(1 + e)      abs err ~2e-7; 2 MUFU + 1.5 packed FP32 ops per element
+// (Replacing the MUFU reciprocal by a bit-trick seed + Halley + Newton step on packed FFMA2 — 7 instead of 3.5 issue
+//  slots per element, half the MUFU work — was measured SLOWER: eval 13.9 -> 15.1 ms.  The epilogue warps are bound
+//  by issue slots, not by the XU pipe.)
 constexpr float kTwoLog2e = 2.8853900817779268f;
 __device__ __forceinline__ float2 tanh_acc2(float2 v, float2 bs) {
     const float2 arg = ffma2(v, make_float2(kTwoLog2e, kTwoLog2e), bs);
