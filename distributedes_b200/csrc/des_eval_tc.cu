@@ -162,6 +162,11 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
     constexpr int kEpiWarps = 8;              // NT == 2: four per tile slot; NT == 1: two per TMEM lane quadrant,
                                               // each taking one 32-column half of every accumulator chunk
     constexpr int kWarpsPerSlot = kEpiWarps / NT;
+    // Pairs with two H1 chunks signal each chunk's readiness separately (h_ready[chunk]; index 1 is otherwise the
+    // second tile slot's barrier, unused when NT == 1): the layer-2 MMAs over the first chunk's k-atoms then run
+    // while the epilogue warps are still producing the second chunk.
+    constexpr bool kChunkedH = PAIR && C::NCH == 2;
+    constexpr int kAtomsPerChunk = kNC / 64;
     constexpr int kMmaWarp = kEpiWarps + kGenWarps;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -286,12 +291,14 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
                             mbar_wait(smem_u32(&bars->acc_empty[ts][st]), ph ^ 1);
                             st_[ts] = st;
                             d_[ts] = slot_base(ts) + C::ACOLS + st * kNC;
-                            if (nc == 0) mbar_wait(smem_u32(&bars->h_ready[ts]), hv[ts] & 1);
+                            if (nc == 0 && !kChunkedH) mbar_wait(smem_u32(&bars->h_ready[ts]), hv[ts] & 1);
                         }
                         tc_fence_after();
                         for (int ka = 0; ka < C::KAT; ++ka) {
                             const uint32_t s = rs, sph = rph;
                             if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
+                            if (kChunkedH && nc == 0 && ka % kAtomsPerChunk == 0)
+                                mbar_wait(smem_u32(&bars->h_ready[ka / kAtomsPerChunk]), hv[0] & 1);
                             mbar_wait(smem_u32(&bars->slot_full[s]), sph);
                             tc_fence_after();
                             const uint32_t bbase = smem_u32(ring + (size_t)s * C::SLOT_BYTES);
@@ -342,6 +349,10 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
                 for (int64_t v = 0; v < rounds; ++v) {
                     mbar_wait(smem_u32(&bars->h_ready[0]), (uint32_t)v & 1);
                     mbar_arrive_cluster(smem_u32(&bars->h_ready[0]), 0);
+                    if (kChunkedH) {
+                        mbar_wait(smem_u32(&bars->h_ready[1]), (uint32_t)v & 1);
+                        mbar_arrive_cluster(smem_u32(&bars->h_ready[1]), 0);
+                    }
                 }
             }
         }
@@ -415,11 +426,19 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
                         tmem_st16(sbase + nc * (kNC / 2) + half * 16, hi);
                         if (X3) tmem_st16(sbase + H / 2 + nc * (kNC / 2) + half * 16, lo);
                     }
+                    if (kChunkedH) {              // this chunk of H1 is complete: its k-atoms may be consumed
+                        tmem_wait_st();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) arrive_leader(&bars->h_ready[nc]);
+                    }
                 }
-                tmem_wait_st();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) arrive_leader(&bars->h_ready[ts]);
+                if (!kChunkedH) {
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) arrive_leader(&bars->h_ready[ts]);
+                }
                 ++hv;
                 // ---------------- epilogue 2+3: H2 = tanh(D2 + b2); a = H2 W3^T + b3 in fp32 registers
                 float2 actp[kMaxA];                          // (even-n, odd-n) partial sums of action q
