@@ -35,6 +35,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// For waits that are long when they happen at all (a producer that ran ahead of its consumer): back off between polls
+// so the waiting warps stay out of the issue slots of the warps they are waiting for (ncu: half of the instructions the
+// generator warps executed were try_wait/NANOSLEEP/BRA of the tight loop above).
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+        asm volatile("nanosleep.u32 %0;" ::"r"(64u));
+    }
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
