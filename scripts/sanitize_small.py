@@ -19,4 +19,11 @@ for (H, T, prec, N) in [(64, 256, 'f16x3', 300), (256, 256, 'f16x3', 200), (256,
 f = torch.randn(20000, device='cuda'); ops.centered_rank(f)
 Y = torch.randn(40, 300, device='cuda'); w = torch.rand(40, device='cuda'); dC = ops.cma_rank_mu(Y, w)
 ops.cma_cov_apply(torch.eye(300, device='cuda'), dC, torch.randn(300, device='cuda'), decay=0.9, c1=0.01, cmu=0.02)
+from distributedes_b200.engine import RolloutEngine
+for H, reps in [(64, 10), (32, 3), (128, 7)]:
+    reng = RolloutEngine(hidden=H, pop_size=9, theta0=StandardFCNet(3, 1, H, seed=0).get_weight(), sigma=0.1, learning_rate=0.1,
+                         repetitions=reps, horizon=25, seed=2, action_noise_std=0.1)
+    for _ in range(2):
+        reng.generation()
+    print('rollout', H, reps, float(reng.fitness_all.mean()), reng.test_returns().mean())
 ops.noise_fill(3, 1001, 1, 2); torch.cuda.synchronize(); print('ok')
