@@ -15,8 +15,10 @@ import time
 
 import numpy as np
 import torch
+import torch.distributed as dist
 
 from . import ops
+from .engine import shard_bounds
 from .utils import StaticNormalizer, logger
 
 
@@ -37,13 +39,32 @@ def cma_constants(n, lam):
 
 class CMAEvolutionStrategy:
     """GPU-resident (mu/mu_w, lambda)-CMA-ES.  C is fp32 (the rank-mu kernel's type); the vectors and the
-    eigen-system are fp64."""
+    eigen-system are fp64.
 
-    def __init__(self, x0, sigma0, popsize, seed=0, device=None):
-        self.device = torch.device(device if device is not None else ('cuda:%d' % torch.cuda.current_device()))
-        if self.device.type != 'cuda':
-            raise RuntimeError('distributedes_b200.cma_es needs a CUDA device: there is no CPU fallback')
+    With torch.distributed initialised the lambda members are sharded contiguously over the ranks: ask()
+    returns the rank's own members (z regenerated from the counter stream, so no solution is ever shipped), tell() takes
+    the local solutions and the GLOBAL cost vector, forms the rank's partial sum_i w_i y_i y_i^T with des_cma_rank_mu and
+    all-reduces the [n, n] partial — the one collective BASELINE.json's north_star names for CMA-ES — plus the n-vector
+    sum_i w_i y_i.  Every rank then applies the identical update, so the strategy state is never broadcast.
+
+    `kernels` (default: distributedes_b200.ops) exists so the world_size > 1 host logic can run under gloo on CPU in the
+    test-suite with an oracle-backed stand-in; the product never runs without the CUDA library."""
+
+    def __init__(self, x0, sigma0, popsize, seed=0, device=None, process_group=None, kernels=None):
+        if kernels is None:
+            self.device = torch.device(device if device is not None else ('cuda:%d' % torch.cuda.current_device()))
+            if self.device.type != 'cuda':
+                raise RuntimeError('distributedes_b200.cma_es needs a CUDA device: there is no CPU fallback')
+            kernels = ops
+        else:
+            self.device = torch.device(device if device is not None else 'cpu')
+        self.kn = kernels
+        self.pg = process_group
+        distributed = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(process_group) if distributed else 1
+        self.rank = dist.get_rank(process_group) if distributed else 0
         self.n, self.lam, self.seed = len(x0), int(popsize), int(seed)
+        self.offset, self.n_local = shard_bounds(self.lam, self.world, self.rank)
         k = cma_constants(self.n, self.lam)
         self.k = k
         dev, f64 = self.device, torch.float64
@@ -61,25 +82,53 @@ class CMAEvolutionStrategy:
         self.chiN = np.sqrt(self.n) * (1 - 1.0 / (4 * self.n) + 1.0 / (21 * self.n * self.n))
 
     def ask(self, z=None):
-        """lambda solutions x_i = m + sigma*B*D*z_i (cma_es.py:62).  z defaults to the counter noise stream
-        (Philox, stream tag 1, counter = (j/4, member, generation)), so shards can regenerate it."""
+        """The rank's solutions x_i = m + sigma*B*D*z_i, i in [offset, offset + n_local) (cma_es.py:62; all lambda of
+        them on a single GPU).  z defaults to the counter noise stream (Philox, stream tag 1, counter = (j/4, member,
+        generation)): a pure function of the member index, so shards regenerate it instead of receiving it."""
         if z is None:
-            z = ops.noise_fill(self.lam, self.n, self.seed, self.gen, stream_tag=1, device=self.device)
+            z = self.kn.noise_fill(self.n_local, self.n, self.seed, self.gen, member_offset=self.offset, stream_tag=1,
+                                   device=self.device)
         self.z = z
         BD = (self.B * self.D).to(torch.float32)                 # columns scaled by D
-        y = z.to(torch.float32) @ BD.T                           # [lambda, n] x [n, n]  (library GEMM)
+        y = z.to(torch.float32) @ BD.T                           # [n_local, n] x [n, n]  (library GEMM)
         self.X = (self.m + self.sigma * y.to(torch.float64)).to(torch.float32).contiguous()
         return self.X
 
+    def gather_cost(self, cost_local):
+        """[lambda] costs from the ranks' shards: all-reduce of the zero-padded vector (== all-gather, ragged allowed)."""
+        cost_local = torch.as_tensor(cost_local, device=self.device, dtype=torch.float32).reshape(-1)
+        if self.world == 1:
+            return cost_local
+        full = torch.zeros(self.lam, dtype=torch.float32, device=self.device)
+        full[self.offset:self.offset + self.n_local] = cost_local
+        dist.all_reduce(full, group=self.pg)
+        return full
+
     def tell(self, solutions, cost):
-        """cma_es.py:90.  solutions [lambda, n] (as returned by ask), cost [lambda] (lower is better; rank-shaped or
-        raw — only the order matters)."""
+        """cma_es.py:90.  solutions: the rank's [n_local, n] (as returned by ask; all lambda on a single GPU),
+        cost [lambda] GLOBAL (lower is better; rank-shaped or raw — only the order matters)."""
         k, n = self.k, self.n
         cost = torch.as_tensor(cost, device=self.device, dtype=torch.float64).reshape(-1)
-        order = torch.sort(cost, stable=True).indices
+        if cost.numel() != self.lam:
+            raise ValueError('tell() needs the cost of all %d members (got %d)' % (self.lam, cost.numel()))
+        order = torch.sort(cost, stable=True).indices                        # identical on every rank
         X = torch.as_tensor(solutions, device=self.device)
-        Y = ((X[order].to(torch.float64) - self.m) / self.sigma)            # y_{i:lambda}
-        yw = self.w64 @ Y
+        if X.shape[0] != self.n_local:
+            raise ValueError('tell() needs this rank\'s %d solutions (got %d)' % (self.n_local, X.shape[0]))
+        # weight of each local member = w[its position in the global order]
+        pos = torch.empty_like(order)
+        pos[order] = torch.arange(self.lam, device=self.device)
+        w_loc64 = self.w64[pos[self.offset:self.offset + self.n_local]]
+        Y = (X.to(torch.float64) - self.m) / self.sigma                       # y_i of the local members
+        yw = w_loc64 @ Y if self.n_local else torch.zeros(n, dtype=torch.float64, device=self.device)
+        # ---- the hot part: rank-mu partial of the shard on our kernel (fp32), summed over ranks
+        if self.n_local:
+            self.kn.cma_rank_mu(Y.to(torch.float32).contiguous(), w_loc64.to(torch.float32).contiguous(), out=self.dC)
+        else:
+            self.dC.zero_()
+        if self.world > 1:
+            dist.all_reduce(self.dC, group=self.pg)                           # the CMA collective of north_star
+            dist.all_reduce(yw, group=self.pg)
         self.m = self.m + self.sigma * yw
         cs, ds, cc, c1, cmu, mu_eff = k['cs'], k['ds'], k['cc'], k['c1'], k['cmu'], k['mu_eff']
         cinv_yw = self.B @ ((self.B.T @ yw) / self.D)
@@ -87,10 +136,8 @@ class CMAEvolutionStrategy:
         norm_ps = float(torch.linalg.norm(self.ps))
         hsig = float(norm_ps / np.sqrt(1 - (1 - cs) ** (2 * (self.gen + 1))) / self.chiN < 1.4 + 2.0 / (n + 1))
         self.pc = (1 - cc) * self.pc + hsig * np.sqrt(cc * (2 - cc) * mu_eff) * yw
-        # ---- the hot part: rank-mu term and covariance update on our kernels (fp32)
-        ops.cma_rank_mu(Y.to(torch.float32).contiguous(), self.w32, out=self.dC)
         decay = 1 + c1 * (1 - hsig) * cc * (2 - cc) - c1 - cmu * float(k['w'].sum())
-        ops.cma_cov_apply(self.C, self.dC, self.pc.to(torch.float32).contiguous(), decay=decay, c1=c1, cmu=cmu)
+        self.kn.cma_cov_apply(self.C, self.dC, self.pc.to(torch.float32).contiguous(), decay=decay, c1=c1, cmu=cmu)
         self.sigma = self.sigma * float(np.exp((cs / ds) * (norm_ps / self.chiN - 1)))
         d2, self.B = torch.linalg.eigh(self.C.to(torch.float64))            # library eigendecomposition (cuSOLVER)
         self.D = torch.sqrt(torch.clamp(d2, min=1e-300))
@@ -130,14 +177,16 @@ def train(config):
     training_timestamps.append(0)
     generation = 0
     while True:
-        solutions = es.ask()                                                                # :62
-        cost = worker.run(solutions)                                                        # :63-72
+        solutions = es.ask()                                                                # :62 (this rank's shard)
+        cost = es.gather_cost(worker.run(solutions))                                        # :63-72, all lambda costs
         total_steps += config.pop_size * config.repetitions * worker.T                      # :73
         best = int(torch.argmin(cost))                                                      # :75
         elapsed_time = time.time() - initial_time
-        test_mean, test_ste = test(config, solutions[best], None, worker=worker)            # :77
-        logger.info('total steps %d, test %f(%f), best %f, elapased time %f' %
-                    (total_steps, test_mean, test_ste, -float(cost.min()), elapsed_time))
+        best_solution = _fetch_member(es, solutions, best)
+        test_mean, test_ste = test(config, best_solution, None, worker=worker)              # :77
+        if es.rank == 0:
+            logger.info('total steps %d, test %f(%f), best %f, elapased time %f' %
+                        (total_steps, test_mean, test_ste, -float(cost.min()), elapsed_time))
         training_rewards.append(test_mean)
         training_steps.append(total_steps)
         training_timestamps.append(elapsed_time)
@@ -149,6 +198,17 @@ def train(config):
         shaped = ops.centered_rank(cost.to(torch.float32).contiguous())                     # :89 fitness_shift(cost)
         es.tell(solutions, shaped)                                                          # :90
     return [training_rewards, training_steps, training_timestamps]
+
+
+def _fetch_member(es, solutions_local, index):
+    """Solution `index` of the global population on every rank (the owner contributes it, the others zeros)."""
+    if es.world == 1:
+        return solutions_local[index]
+    row = torch.zeros(es.n, dtype=torch.float32, device=es.device)
+    if es.offset <= index < es.offset + es.n_local:
+        row.copy_(solutions_local[index - es.offset])
+    dist.all_reduce(row, group=es.pg)
+    return row
 
 
 def test(config, solution, stats, worker=None):

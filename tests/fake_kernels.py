@@ -126,3 +126,24 @@ def obs_stats_merge_totals(stats, totals, state_dim):
     m, v, n = po.merge_totals((a[:d0], a[d0:2 * d0], a[2 * d0]), t[:d0], t[d0:2 * d0], t[2 * d0])
     stats.copy_(torch.from_numpy(np.concatenate([m, v, [n]]).astype(np.float32)))
     return stats
+
+
+# ---- CMA (for cma_es.CMAEvolutionStrategy under gloo) ------------------------------------------------------------------
+def noise_fill(n_members, P, seed, generation, member_offset=0, stream_tag=0, device='cpu'):
+    return torch.from_numpy(orc.noise(seed, generation, member_offset, n_members, P, stream=stream_tag).astype(np.float32))
+
+
+def cma_rank_mu(Y, w, out=None):
+    from oracle import cma_oracle as cma
+    res = torch.from_numpy(cma.rank_mu_delta(Y.numpy().astype(np.float64), w.numpy().astype(np.float64)).astype(np.float32))
+    if out is None:
+        return res
+    out.copy_(res)
+    return out
+
+
+def cma_cov_apply(Cmat, dC, pc, *, decay, c1, cmu):
+    p = pc.numpy().astype(np.float64)
+    new = decay * Cmat.numpy().astype(np.float64) + c1 * np.outer(p, p) + cmu * dC.numpy().astype(np.float64)
+    Cmat.copy_(torch.from_numpy(new.astype(np.float32)))
+    return Cmat

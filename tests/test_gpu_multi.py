@@ -68,3 +68,47 @@ def test_two_gpu_generation_matches_one_gpu(N, precision, use_graph):
     th0 = orc.synthetic_theta(d0, H, A)
     th1 = one.theta.cpu().numpy()
     assert np.linalg.norm(th1 - res[0][3]) <= 1e-5 * np.linalg.norm(th1 - th0)
+
+
+def _cma_worker(rank, world, port, outdir):
+    sys.path.insert(0, REPO)
+    from distributedes_b200.cma_es import CMAEvolutionStrategy
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world,
+                            device_id=torch.device('cuda', rank))
+    try:
+        n, lam = 512, 130                                   # ragged shards
+        m0 = np.random.RandomState(0).randn(n)
+        es = CMAEvolutionStrategy(m0, 1.0, lam, seed=6, device='cuda:%d' % rank)
+        X = es.ask()
+        cost = es.gather_cost((X.double() ** 2).sum(1).float())
+        es.tell(X, cost)
+        torch.cuda.synchronize()
+        np.savez(os.path.join(outdir, 'cma%d.npz' % rank), C=es.C.cpu().numpy(), m=es.m.cpu().numpy(), sigma=es.sigma,
+                 X=X.cpu().numpy(), cost=cost.cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_cma_generation_matches_one_gpu():
+    """cma_es.CMAEvolutionStrategy sharded over 2 GPUs (all-reduce of the [n,n] rank-mu partials) against the same
+    generation on one GPU: generation 0 has B = I, so both sample identical solutions from the counter noise."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    sys.path.insert(0, REPO)
+    from distributedes_b200.cma_es import CMAEvolutionStrategy
+    import tempfile
+    with tempfile.TemporaryDirectory() as outdir:
+        mp.spawn(_cma_worker, args=(2, 29761, outdir), nprocs=2, join=True)
+        r = [np.load(os.path.join(outdir, 'cma%d.npz' % k)) for k in range(2)]
+    for k in ('C', 'm', 'sigma', 'cost'):
+        assert np.array_equal(r[0][k], r[1][k]), k
+    n, lam = 512, 130
+    one = CMAEvolutionStrategy(np.random.RandomState(0).randn(n), 1.0, lam, seed=6, device='cuda:0')
+    X = one.ask()
+    assert np.array_equal(X.cpu().numpy(), np.concatenate([r[0]['X'], r[1]['X']]))
+    cost = (X.double() ** 2).sum(1).float()
+    one.tell(X, cost)
+    C1 = one.C.cpu().numpy()
+    assert np.linalg.norm(C1 - r[0]['C']) <= 1e-6 * np.linalg.norm(C1)          # order of the cross-shard fp32 sum
+    assert np.linalg.norm(one.m.cpu().numpy() - r[0]['m']) <= 1e-12 * np.linalg.norm(r[0]['m'])
