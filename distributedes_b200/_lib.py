@@ -58,6 +58,9 @@ SIGNATURES = {
     'des_state_advance': (C.c_int, [_P, _D, _D, _P]),
     'des_cma_rank_mu': (C.c_int, [_P, _P, _P, _I64, _I64, _P]),
     'des_cma_cov_apply': (C.c_int, [_P, _P, _P, _I64, _D, _D, _D, _P]),
+    'des_cma_packed_elems': (_I64, [_I64]),
+    'des_cma_rank_mu_packed': (C.c_int, [_P, _P, _P, _I64, _I64, _P]),
+    'des_cma_cov_apply_packed': (C.c_int, [_P, _P, _P, _I64, _D, _D, _D, _P]),
     'des_session_create': (C.c_int, [C.POINTER(_P), C.c_int, Dims, _I64, _I64, _I64, Opt, _D, _U64, C.c_int, _P]),
     'des_session_destroy': (None, [_P]),
     'des_session_generation_host': (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),

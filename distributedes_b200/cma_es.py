@@ -121,13 +121,27 @@ class CMAEvolutionStrategy:
         w_loc64 = self.w64[pos[self.offset:self.offset + self.n_local]]
         Y = (X.to(torch.float64) - self.m) / self.sigma                       # y_i of the local members
         yw = w_loc64 @ Y if self.n_local else torch.zeros(n, dtype=torch.float64, device=self.device)
-        # ---- the hot part: rank-mu partial of the shard on our kernel (fp32), summed over ranks
-        if self.n_local:
-            self.kn.cma_rank_mu(Y.to(torch.float32).contiguous(), w_loc64.to(torch.float32).contiguous(), out=self.dC)
+        # ---- the hot part: rank-mu partial of the shard on our kernel (fp32), summed over ranks.  Sharded runs keep the
+        # partial as packed upper-triangular tiles: the all-reduce moves half the bytes of the [n, n] matrix and the
+        # covariance update mirrors the tiles while applying them.
+        packed = self.world > 1 and hasattr(self.kn, 'cma_rank_mu_packed')
+        Y32, w32 = Y.to(torch.float32).contiguous(), w_loc64.to(torch.float32).contiguous()
+        if packed:
+            if getattr(self, 'dC_tiles', None) is None:
+                self.dC_tiles = torch.zeros(self.kn.cma_packed_elems(n), dtype=torch.float32, device=self.device)
+            if self.n_local:
+                self.kn.cma_rank_mu_packed(Y32, w32, out=self.dC_tiles)
+            else:
+                self.dC_tiles.zero_()
+            dist.all_reduce(self.dC_tiles, group=self.pg)                     # the CMA collective of north_star
         else:
-            self.dC.zero_()
+            if self.n_local:
+                self.kn.cma_rank_mu(Y32, w32, out=self.dC)
+            else:
+                self.dC.zero_()
+            if self.world > 1:
+                dist.all_reduce(self.dC, group=self.pg)
         if self.world > 1:
-            dist.all_reduce(self.dC, group=self.pg)                           # the CMA collective of north_star
             dist.all_reduce(yw, group=self.pg)
         self.m = self.m + self.sigma * yw
         cs, ds, cc, c1, cmu, mu_eff = k['cs'], k['ds'], k['cc'], k['c1'], k['cmu'], k['mu_eff']
@@ -137,7 +151,11 @@ class CMAEvolutionStrategy:
         hsig = float(norm_ps / np.sqrt(1 - (1 - cs) ** (2 * (self.gen + 1))) / self.chiN < 1.4 + 2.0 / (n + 1))
         self.pc = (1 - cc) * self.pc + hsig * np.sqrt(cc * (2 - cc) * mu_eff) * yw
         decay = 1 + c1 * (1 - hsig) * cc * (2 - cc) - c1 - cmu * float(k['w'].sum())
-        self.kn.cma_cov_apply(self.C, self.dC, self.pc.to(torch.float32).contiguous(), decay=decay, c1=c1, cmu=cmu)
+        pc32 = self.pc.to(torch.float32).contiguous()
+        if packed:
+            self.kn.cma_cov_apply_packed(self.C, self.dC_tiles, pc32, decay=decay, c1=c1, cmu=cmu)
+        else:
+            self.kn.cma_cov_apply(self.C, self.dC, pc32, decay=decay, c1=c1, cmu=cmu)
         self.sigma = self.sigma * float(np.exp((cs / ds) * (norm_ps / self.chiN - 1)))
         d2, self.B = torch.linalg.eigh(self.C.to(torch.float64))            # library eigendecomposition (cuSOLVER)
         self.D = torch.sqrt(torch.clamp(d2, min=1e-300))

@@ -283,3 +283,30 @@ def cma_cov_apply(Cmat, dC, pc, *, decay, c1, cmu):
                                                  _ptr(pc, torch.float32, 'pc', allow_none=True), n, decay, c1, cmu,
                                                  _stream()), 'des_cma_cov_apply')
     return Cmat
+
+
+def cma_packed_elems(n):
+    return int(_lib.load().des_cma_packed_elems(int(n)))
+
+
+def cma_rank_mu_packed(Y, w, out=None):
+    """The rank-mu partial as packed upper-triangular tiles (the multi-GPU all-reduce payload: half of [n, n])."""
+    lam, n = Y.shape
+    if w.numel() != lam:
+        raise RuntimeError('w has %d entries, Y has %d rows' % (w.numel(), lam))
+    if out is None:
+        out = torch.empty(cma_packed_elems(n), dtype=torch.float32, device=Y.device)
+    with _on(Y, 'Y'):
+        _lib.check(_lib.load().des_cma_rank_mu_packed(_ptr(out, torch.float32, 'out'), _ptr(Y, torch.float32, 'Y'),
+                                                      _ptr(w, torch.float32, 'w'), lam, n, _stream()), 'des_cma_rank_mu_packed')
+    return out
+
+
+def cma_cov_apply_packed(Cmat, tiles, pc, *, decay, c1, cmu):
+    """C <- decay*C + c1*pc pc^T + cmu*dC with dC as packed upper tiles, in place."""
+    n = Cmat.shape[0]
+    with _on(Cmat, 'C'):
+        _lib.check(_lib.load().des_cma_cov_apply_packed(_ptr(Cmat, torch.float32, 'C'), _ptr(tiles, torch.float32, 'tiles'),
+                                                        _ptr(pc, torch.float32, 'pc', allow_none=True), n, decay, c1, cmu,
+                                                        _stream()), 'des_cma_cov_apply_packed')
+    return Cmat

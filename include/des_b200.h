@@ -226,6 +226,17 @@ DES_API int des_cma_rank_mu(float *dC_out_dev, const float *Y_dev, const float *
 DES_API int des_cma_cov_apply(float *C_dev, const float *dC_dev, const float *pc_dev, int64_t n, double decay,
                       double c1, double cmu, void *stream);
 
+/* The same two steps with the rank-mu partial kept as PACKED upper-triangular tiles — the payload to all-reduce across
+ * ranks when lambda is sharded (half the bytes of the [n][n] matrix).  Layout: tiles (bi <= bj) in row-major
+ * order of (bi, bj), each [tile][tile] row-major with tile = 64 (n <= 2048) or 128; entries beyond n are zero.
+ * des_cma_packed_elems(n) floats.  des_cma_cov_apply_packed mirrors the tiles while applying them (diagonal tiles take the
+ * j >= i entry for both sides: C stays exactly symmetric). */
+DES_API int64_t des_cma_packed_elems(int64_t n);
+DES_API int des_cma_rank_mu_packed(float *tiles_out_dev, const float *Y_dev, const float *w_dev, int64_t lambda_local,
+                                   int64_t n, void *stream);
+DES_API int des_cma_cov_apply_packed(float *C_dev, const float *tiles_dev, const float *pc_dev, int64_t n, double decay,
+                                     double c1, double cmu, void *stream);
+
 /* ---- host-buffer session: the call a reference-side binding makes --------------------------- */
 
 typedef struct des_session des_session;   /* opaque; owns device buffers + a stream */

@@ -19,7 +19,16 @@ w = torch.rand(nl, device=dev) / lam
 C = torch.eye(n, device=dev); pc = torch.randn(n, device=dev); dC = torch.empty(n, n, device=dev)
 
 
-def step(collective=True):
+tiles = torch.empty(ops.cma_packed_elems(n), device=dev)
+
+
+def step(collective=True, packed=False):
+    if packed:          # upper-triangular tiles: half the all-reduce payload (what cma_es.CMAEvolutionStrategy uses)
+        ops.cma_rank_mu_packed(Y, w, out=tiles)
+        if world > 1 and collective:
+            dist.all_reduce(tiles)
+        ops.cma_cov_apply_packed(C, tiles, pc, decay=0.99, c1=1e-4, cmu=1e-3)
+        return
     ops.cma_rank_mu(Y, w, out=dC)
     if world > 1 and collective:
         dist.all_reduce(dC)
@@ -46,9 +55,12 @@ def timed(fn, k=20):
 full = timed(step)
 compute = timed(lambda: step(False))
 ar = timed(lambda: dist.all_reduce(dC)) if world > 1 else 0.0
+full_p = timed(lambda: step(True, True))
+compute_p = timed(lambda: step(False, True))
+ar_p = timed(lambda: dist.all_reduce(tiles)) if world > 1 else 0.0
 if rank == 0:
     print(json.dumps(dict(workload='CMA rank-mu update n=4096 lambda=1024', n_gpus=world, members_per_gpu=nl,
                           ms_per_update=full, updates_per_sec=1e3 / full, compute_only_ms=compute, allreduce_only_ms=ar,
-                          allreduce_bytes=4 * n * n, fp32_tflops_counted_2lambda_n2=2.0 * lam * n * n / full / 1e9)))
+                          allreduce_bytes=4 * n * n, packed=dict(ms_per_update=full_p, updates_per_sec=1e3 / full_p, compute_only_ms=compute_p, allreduce_only_ms=ar_p, allreduce_bytes=4 * tiles.numel()), fp32_tflops_counted_2lambda_n2=2.0 * lam * n * n / full / 1e9)))
 if world > 1:
     dist.destroy_process_group()

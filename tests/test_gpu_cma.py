@@ -127,3 +127,28 @@ def test_pop_eval_and_cma_train_surface():
     rewards, steps, stamps = cma_es.train(cfg)
     assert len(rewards) == len(steps) == len(stamps) == 4 and steps[0] == 0 and steps[1] == 64 * 64
     assert np.all(np.isfinite(rewards)) and np.all(np.diff(stamps) >= 0)
+
+
+@pytest.mark.parametrize('n,lam', [(300, 40), (1024, 64), (2500, 24), (4096, 16)])
+def test_packed_rank_mu_and_apply_equal_the_full_matrix_path(n, lam):
+    """des_cma_rank_mu_packed + des_cma_cov_apply_packed (the sharded runs' path: the all-reduce payload is the packed
+    upper triangle) produce exactly the C of des_cma_rank_mu + des_cma_cov_apply, and C stays exactly symmetric."""
+    from distributedes_b200 import ops
+    g = torch.Generator(device='cpu').manual_seed(n)
+    Y = torch.randn(lam, n, generator=g).to(DEV)
+    w = torch.rand(lam, generator=g).to(DEV)
+    pc = torch.randn(n, generator=g).to(DEV)
+    A = torch.randn(n, n, generator=g)
+    S = A @ A.T / n
+    C0 = (0.5 * (S + S.T)).to(DEV).contiguous()               # exactly symmetric input
+    C1, C2 = C0.clone(), C0.clone()
+    dC = ops.cma_rank_mu(Y, w)
+    ops.cma_cov_apply(C1, dC, pc, decay=0.9, c1=0.01, cmu=0.05)
+    tiles = ops.cma_rank_mu_packed(Y, w)
+    assert tiles.numel() == ops.cma_packed_elems(n)
+    ops.cma_cov_apply_packed(C2, tiles, pc, decay=0.9, c1=0.01, cmu=0.05)
+    assert torch.equal(C1, C2)
+    # without the rank-one term (whose fp32 product (c1 pc_i) pc_j is not symmetric in either path) C stays exactly symmetric
+    C3 = C0.clone()
+    ops.cma_cov_apply_packed(C3, tiles, None, decay=0.9, c1=0.0, cmu=0.05)
+    assert torch.equal(C3, C3.T)
