@@ -148,6 +148,35 @@ def test_config_surface_matches_reference_attributes():
     assert (b.state_dim, b.action_dim, len(b.initial_weight)) == (24, 4, 6020)
 
 
+def test_closed_loop_config_and_validation_without_gpu(lib):
+    """ClosedLoopPendulumConfig keeps the reference's PendulumConfig values (config.py:8-9, 26-31); the device environment
+    has no host-side step; des_rollout_eval / the packed CMA entry points validate their arguments before touching CUDA."""
+    from distributedes_b200 import _lib
+    from distributedes_b200.config import ClosedLoopPendulumConfig
+    c = ClosedLoopPendulumConfig(64)
+    assert (c.task, c.state_dim, c.action_dim, len(c.initial_weight)) == ('Pendulum-v0', 3, 1, 4481)
+    assert (c.repetitions, c.test_repetitions, c.clip, c.closed_loop, c.normalize_obs) == (10, 10, 2.0, True, True)
+    with pytest.raises(RuntimeError, match='stepped on the GPU'):
+        c.env_fn().reset()
+    d = _lib.Dims(3, 64, 1, 200)
+    rc = lib.des_rollout_eval(None, None, None, None, None, 7, d, 10, 0.1, 2.0, 0.0, 0, 0, None, 0, 4, 0, None, 0, None)
+    assert rc == -1 and b'unknown environment' in lib.des_last_error()
+    rc = lib.des_rollout_eval(None, None, None, None, None, 0, _lib.Dims(3, 48, 1, 200), 10, 0.1, 2.0, 0.0, 0, 0, None, 0, 4, 0,
+                              None, 0, None)
+    assert rc == -1 and b'multiple of 32' in lib.des_last_error()
+    rc = lib.des_rollout_eval(None, None, None, None, None, 0, d, 11, 0.1, 2.0, 0.0, 0, 0, None, 0, 4, 0, None, 0, None)
+    assert rc == -1 and b'repetitions' in lib.des_last_error()
+    rc = lib.des_rollout_eval(None, None, None, None, None, 0, d, 10, 0.1, 2.0, 0.0, 0, 0, None, 0, 4, 0, None, 0, None)
+    assert rc == -1 and b'NULL' in lib.des_last_error()
+    assert lib.des_rollout_eval(None, None, None, None, None, 0, d, 10, 0.1, 2.0, 0.0, 0, 0, None, 0, 0, 0, None, 0, None) == 0
+    # packed CMA payload: upper-triangular tiles of 64 (n <= 2048) or 128
+    assert lib.des_cma_packed_elems(1024) == 16 * 17 // 2 * 64 * 64
+    assert lib.des_cma_packed_elems(4096) == 32 * 33 // 2 * 128 * 128
+    assert lib.des_cma_packed_elems(300) == 5 * 6 // 2 * 64 * 64 and lib.des_cma_packed_elems(0) == 0
+    assert lib.des_cma_rank_mu_packed(None, None, None, 4, 16, None) == -1
+    assert lib.des_cma_cov_apply_packed(None, None, None, 16, 1.0, 0.0, 0.0, None) == -1
+
+
 def test_product_never_touches_the_oracle():
     """oracle/ is test infrastructure: nothing under distributedes_b200/ (nor the GPU arm of bench.py) may import it."""
     import glob
