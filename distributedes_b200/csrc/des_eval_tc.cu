@@ -1,14 +1,16 @@
 // des_nes_eval, precision DES_FWD_F16 / DES_FWD_F16X3: fused sample + perturb + forward + fitness with the two
 // hidden-layer GEMMs on tcgen05 tensor cores.
 //
-// One persistent CTA per SM walks its members (Worker.run natural_es.py:27-32 per member).  For a member
-// and a tile of 128 observations (M = 128 rows = TMEM lanes), StandardFCNet.forward (model.py:34-39) is
+// One persistent CTA per SM (or one CTA PAIR per two SMs, see TcCfg) walks its members (Worker.run
+// natural_es.py:27-32 per member).  For a member and a tile of 128 observations (M = 128 rows = TMEM lanes),
+// StandardFCNet.forward (model.py:34-39) is
 //
-//   D1 = X  W1'^T            tcgen05.mma kind::f16, A = X  (fp16, resident in TMEM), B = W1' tiles (smem)
-//   H1 = tanh(D1 + b1')      epilogue warps: TMEM -> regs -> tanh -> fp16 -> TMEM (A operand of layer 2)
-//   D2 = H1 W2'^T            tcgen05.mma, A = H1 (TMEM), B = W2' tiles (smem ring)
+//   D1 = X  W1'^T            tcgen05.mma kind::f16, SS: A = X tile (fp16, shared memory, resident for the whole
+//                            kernel), B = W1' tiles (shared-memory ring)
+//   H1 = tanh(D1 + b1')      epilogue warps: TMEM -> regs -> tanh -> fp16 -> TMEM (the A operand of layer 2)
+//   D2 = H1 W2'^T            tcgen05.mma, TS: A = H1 (TMEM), B = W2' tiles (shared-memory ring)
 //   H2 = tanh(D2 + b2')      epilogue warps, registers only
-//   a  = H2 W3'^T + b3'      A <= 8 outputs: exact fp32 FFMA in the same epilogue pass (no third MMA)
+//   a  = H2 W3'^T + b3'      A <= 8 outputs: exact fp32 FFMA2 in the same epilogue pass (no third MMA)
 //   fitness += -|| clip(a) - a* ||^2                                              (utils.py:134-137)
 //
 // W' = fp32(theta + sigma*eps) (natural_es.py:28-30) is never stored in HBM: generator warps regenerate
@@ -18,17 +20,18 @@
 // Precision modes
 //   F16    operands rounded to fp16 (11 significant bits, as TF32), fp32 accumulate, MUFU tanh.approx.
 //   F16X3  every operand split x = hi + lo (fp16 each, ~22 bits); D += A_hi B_hi + A_lo B_hi + A_hi B_lo;
-//          accurate tanh.  ~fp32 accuracy at 3 MMAs per k-step.
+//          tanh as 1 - 2/(1 + 2^(2x log2 e)) on packed f32x2 ops.  ~fp32 accuracy at 3 MMAs per k-step.
 //
 // Warp roles (aligned to warpgroups so setmaxnreg can move registers from generators to epilogue warps):
-// warps [0, 4*NT) = epilogue (warp w owns TMEM lane quadrant w%4 of tile slot w/4); the next 16 warps =
-// weight generators; the last warp = TMEM allocator + single-thread MMA issuer.  X (the observation tape,
-// fp16, K padded to 64) sits in shared memory as the layer-1 A operand for the whole kernel.  All hand-offs
-// are mbarriers (generator -> MMA: slot_full/empty; MMA -> epilogue: acc_full/empty; epilogue -> MMA:
-// h_ready / h_free); accumulators are double buffered in TMEM in chunks of 64 columns.
+// warps 0-7 = epilogue (NT == 2: warp w owns TMEM lane quadrant w%4 of tile slot w/4; NT == 1: two warps per
+// quadrant, each taking every other 32-column group), warps 8-23 = weight generators, warp 24 = TMEM allocator +
+// single-thread MMA issuer (+ three relay lanes in the follower CTA of a pair).  All hand-offs are mbarriers
+// (generator -> MMA: slot_full/empty; MMA -> epilogue: acc_full/empty; epilogue -> MMA: h_ready / h_free);
+// accumulators are double buffered in TMEM in chunks of NC columns.
 //
-// Bounds per member-tile: RNG issue (~20 instr/normal), MUFU (2/normal + 1-2/tanh), tensor
-// (2*128*(d0*H + H*H) flop; x3 in F16X3).  See DESIGN.md for the budget and measured numbers.
+// Measured (ncu, profiles/README.md): a latency-bound three-stage pipeline — ~26 useful instructions per normal
+// deviate in the generators, 2 MUFU + 4.5 other instructions per hidden activation in the f16x3 epilogue, tensor
+// pipe 25 % busy; DRAM traffic < 1 MB per launch.
 #include <stdlib.h>
 #include "des_common.cuh"
 #include "des_tc.cuh"
