@@ -365,7 +365,9 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
         const int ts = (NT == 2) ? (warp >> 2) : 0;                   // tile slot
         const int my_half = warp >> 2;                                // NT == 1: this warp owns the 32-column groups g with (g & 1) == my_half
         constexpr int kGroups = kNC / 32;                             // 32-column groups per accumulator chunk
-        const int last_g = (NT == 2) ? kGroups - 1 : kGroups - 2 + my_half;   // after loading it, the stage is free
+        // this warp's share of an accumulator chunk as 16-column steps: group g = (NT == 2 ? s/2 : 2*(s/2) + my_half)
+        constexpr int kSteps = 2 * ((NT == 2) ? kGroups : kGroups / 2);
+        auto step_col = [&](int s) { return ((NT == 2) ? (s >> 1) : 2 * (s >> 1) + my_half) * 32 + (s & 1) * 16; };
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
         const int row = (warp & 3) * 32 + lane;                       // observation row inside the tile
         uint32_t acc_u = 0, hv = 0, mi = 0;
@@ -382,52 +384,48 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
                     const uint32_t u = acc_u++, st = u & 1, ph = (u >> 1) & 1;
                     mbar_wait(smem_u32(&bars->acc_full[ts][st]), ph);
                     tc_fence_after();
+                    // 16-column steps, software pipelined: the tcgen05.ld of step s+1 is in flight while step s is
+                    // computed (the TMEM read latency was 14 % of the epilogue warps' busy time)
+                    const uint32_t acc_base = sbase + C::ACOLS + st * kNC;
+                    uint32_t vbuf[2][16];
+                    tmem_ld16(acc_base + step_col(0), vbuf[0]);
 #pragma unroll
-                    for (int half = 0; half < kGroups; ++half) {            // `half` = 32-column group of the chunk
-                        if (NT == 1 && (half & 1) != my_half) continue;
-                        uint32_t v[32];
-                        tmem_ld32(sbase + C::ACOLS + st * kNC + half * 32, v);
-                        tmem_wait_ld();
-                        if (half == last_g) {
+                    for (int s = 0; s < kSteps; ++s) {
+                        uint32_t (&v)[16] = vbuf[s & 1];
+                        tmem_wait_ld16(v);
+                        if (s + 1 < kSteps) {
+                            tmem_ld16(acc_base + step_col(s + 1), vbuf[(s + 1) & 1]);
+                        } else {                                   // every load of this accumulator stage has landed
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) arrive_leader(&bars->acc_empty[ts][st]);
                         }
-                        if (nc == 0 && half == ((NT == 2) ? 0 : my_half)) {
+                        if (nc == 0 && s == 0) {
                             // the previous (member, pass) must have finished reading H1 before we overwrite it
                             mbar_wait(smem_u32(&bars->h_free[ts]), (hv & 1) ^ 1);
                             tc_fence_after();
                         }
-                        uint32_t hi[16], lo[16];
-                        if (X3) {       // b1 holds b * 2log2(e) in this mode (see the generator)
-                            const float4 *bq = reinterpret_cast<const float4 *>(b1 + nc * kNC + half * 32);
+                        const int col = step_col(s);
+                        const float4 *bq = reinterpret_cast<const float4 *>(b1 + nc * kNC + col);
+                        uint32_t hi[8], lo[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float4 b = bq[i];
-                                const float2 h01 = tanh_acc2(make_float2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])),
-                                                             make_float2(b.x, b.y));
-                                const float2 h23 = tanh_acc2(make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])),
-                                                             make_float2(b.z, b.w));
-                                split_h2p(h01, hi[2 * i], lo[2 * i]);
-                                split_h2p(h23, hi[2 * i + 1], lo[2 * i + 1]);
-                            }
-                        } else {
-                            // (tanh.approx.f16x2 was tried here: SASS issues one MUFU.TANH.F16 per half plus a PRMT,
-                            //  so it saves nothing over fp32 MUFU.TANH and costs precision)
-                            const float4 *bq = reinterpret_cast<const float4 *>(b1 + nc * kNC + half * 32);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float4 b = bq[i];
-                                const float2 x01 = fadd2(make_float2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])),
-                                                         make_float2(b.x, b.y));
-                                const float2 x23 = fadd2(make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])),
-                                                         make_float2(b.z, b.w));
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 b = bq[i];
+                            const float2 v01 = make_float2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]));
+                            const float2 v23 = make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                            if (X3) {       // b1 holds b * 2log2(e) in this mode (see the generator)
+                                split_h2p(tanh_acc2(v01, make_float2(b.x, b.y)), hi[2 * i], lo[2 * i]);
+                                split_h2p(tanh_acc2(v23, make_float2(b.z, b.w)), hi[2 * i + 1], lo[2 * i + 1]);
+                            } else {
+                                // (tanh.approx.f16x2 was tried here: SASS issues one MUFU.TANH.F16 per half plus a PRMT,
+                                //  so it saves nothing over fp32 MUFU.TANH and costs precision)
+                                const float2 x01 = fadd2(v01, make_float2(b.x, b.y)), x23 = fadd2(v23, make_float2(b.z, b.w));
                                 hi[2 * i] = pack_h2(tanh_fast(x01.x), tanh_fast(x01.y));
                                 hi[2 * i + 1] = pack_h2(tanh_fast(x23.x), tanh_fast(x23.y));
                             }
                         }
-                        tmem_st16(sbase + nc * (kNC / 2) + half * 16, hi);
-                        if (X3) tmem_st16(sbase + H / 2 + nc * (kNC / 2) + half * 16, lo);
+                        tmem_st8(sbase + nc * (kNC / 2) + col / 2, hi);
+                        if (X3) tmem_st8(sbase + H / 2 + nc * (kNC / 2) + col / 2, lo);
                     }
                     if (kChunkedH) {              // this chunk of H1 is complete: its k-atoms may be consumed
                         tmem_wait_st();
@@ -451,21 +449,24 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
                     const uint32_t u = acc_u++, st = u & 1, ph = (u >> 1) & 1;
                     mbar_wait(smem_u32(&bars->acc_full[ts][st]), ph);
                     tc_fence_after();
+                    const uint32_t acc_base = sbase + C::ACOLS + st * kNC;
+                    uint32_t vbuf[2][16];
+                    tmem_ld16(acc_base + step_col(0), vbuf[0]);
 #pragma unroll
-                    for (int half = 0; half < kGroups; ++half) {
-                        if (NT == 1 && (half & 1) != my_half) continue;
-                        uint32_t v[32];
-                        tmem_ld32(sbase + C::ACOLS + st * kNC + half * 32, v);
-                        tmem_wait_ld();
-                        if (half == last_g) {
+                    for (int s = 0; s < kSteps; ++s) {
+                        uint32_t (&v)[16] = vbuf[s & 1];
+                        tmem_wait_ld16(v);
+                        if (s + 1 < kSteps) {
+                            tmem_ld16(acc_base + step_col(s + 1), vbuf[(s + 1) & 1]);
+                        } else {
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) arrive_leader(&bars->acc_empty[ts][st]);
                         }
-                        const int n0 = nc * kNC + half * 32;
+                        const int n0 = nc * kNC + step_col(s);
                         const float4 *bq = reinterpret_cast<const float4 *>(b2 + n0);
 #pragma unroll
-                        for (int i4 = 0; i4 < 8; ++i4) {
+                        for (int i4 = 0; i4 < 4; ++i4) {
                             const float4 b = bq[i4];
                             const float2 v01 = make_float2(__uint_as_float(v[4 * i4]), __uint_as_float(v[4 * i4 + 1]));
                             const float2 v23 = make_float2(__uint_as_float(v[4 * i4 + 2]), __uint_as_float(v[4 * i4 + 3]));
