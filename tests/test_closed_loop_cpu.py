@@ -91,3 +91,40 @@ def test_rollout_engine_sharded_equals_single_process():
     assert np.allclose(res[0]['stats'], recs[-1]['stats'], rtol=1e-5, atol=1e-6)
     assert np.allclose(res[0]['tests'][1], recs[1]['test'], rtol=1e-6)
     assert np.max(np.abs(res[0]['theta'] - recs[-1]['theta'])) <= 2e-6
+
+
+def _train_worker(rank, world, port, outdir):
+    """natural_es.train() — the reference-facing loop — on two ranks under gloo, closed loop, oracle-backed kernels."""
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, 'tests'))
+    import fake_kernels
+    from distributedes_b200 import natural_es
+    from distributedes_b200.config import ClosedLoopPendulumConfig
+    torch.set_num_threads(1)
+    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    try:
+        g = np.load(GOLD)
+        cfg = ClosedLoopPendulumConfig(hidden_size=int(g['H']))
+        cfg.initial_weight = g['theta0'].copy()
+        cfg.pop_size, cfg.sigma, cfg.learning_rate, cfg.seed = int(g['N']), float(g['sigma']), float(g['lr']), int(g['seed'])
+        cfg.max_steps = (int(g['gens']) + 1) * cfg.pop_size * cfg.repetitions * 200 - 1
+        eng = natural_es.build_engine(cfg, device='cpu', kernels=fake_kernels)
+        rewards, steps, stamps = natural_es.train(cfg, engine=eng)
+        np.savez(os.path.join(outdir, 'train%d.npz' % rank), rewards=np.asarray(rewards), steps=np.asarray(steps),
+                 theta=eng.theta.numpy(), n_stamps=len(stamps))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_train_surface_on_two_ranks_reproduces_the_reference_golden():
+    """BASELINE configs[0] through natural_es.train(ClosedLoopPendulumConfig) on 2 ranks (8 members each): the returned
+    [rewards, steps, timestamps] triple and the final parameters equal the reference's verbatim run."""
+    g = np.load(GOLD)
+    with tempfile.TemporaryDirectory() as outdir:
+        mp.spawn(_train_worker, args=(2, 29683, outdir), nprocs=2, join=True)
+        r = [np.load(os.path.join(outdir, 'train%d.npz' % k)) for k in range(2)]
+    for k in ('rewards', 'steps', 'theta'):
+        assert np.array_equal(r[0][k], r[1][k]), k
+    assert list(r[0]['steps']) == list(g['train_steps']) and int(r[0]['n_stamps']) == len(g['train_steps'])
+    assert np.allclose(r[0]['rewards'], g['test_rewards'], rtol=1e-5)
+    assert np.max(np.abs(r[0]['theta'] - g['theta'][-1])) <= 2e-6
