@@ -39,7 +39,7 @@ __device__ __forceinline__ double unit_open(uint32_t x) { return ((double)(x & 0
 struct Pendulum {
     double th, thdot, sn, cs;
     __device__ void reset(uint32_t rep, uint32_t member, uint32_t gen, const PhiloxKey &key) {
-        const uint4 x = philox4x32_10(rep, member, gen, kStreamEnvReset, key);
+        const uint4 x = philox4x32(rep, member, gen, kStreamEnvReset, key);
         th = (2.0 * unit_open(x.x) - 1.0) * 3.141592653589793;        // uniform(-pi, pi)
         thdot = (2.0 * unit_open(x.y) - 1.0) * 1.0;                     // uniform(-1, 1)
     }
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(32) rollout_pendulum_kernel(RollArgs a) {
         for (int c = 1; c < C; ++c) act = (csel == c) ? p[c] : act;
         act += b3;
         if (a.act_noise != 0.f) {                                        // utils.py:133
-            const uint4 xr = philox4x32_10((uint32_t)t, member * 16u + (uint32_t)ep, gen, kStreamActNoise, a.key);
+            const uint4 xr = philox4x32((uint32_t)t, member * 16u + (uint32_t)ep, gen, kStreamActNoise, a.key);
             float z0, z1;
             box_muller(xr.x, xr.y, z0, z1);
             act = __fmaf_rn(z0, a.act_noise, act);

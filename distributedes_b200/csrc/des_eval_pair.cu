@@ -1,0 +1,744 @@
+// des_nes_eval, tensor-core path for CTA pairs (cta_group::2), tape of exactly 256 observations, hidden width 128 or
+// 256: the headline shape (BASELINE configs[3]: 2x256 MLP, pop 65 536).  Same arithmetic as des_eval_tc.cu
+// (Worker.run natural_es.py:27-32 per member; StandardFCNet.forward model.py:34-39; fitness utils.py:134-137), a
+// different pipeline, built from the round-1 ncu evidence (profiles/README.md §3: the epilogue warps were the critical
+// path, the tensor pipe idled while they worked, and the XU (MUFU) pipe was the busiest unit):
+//
+//   * D1 is converted to H1 IN PLACE in tensor memory.  Layer 1 accumulates D1 = X W1'^T (fp32, one column per hidden
+//     unit) straight into the columns that will hold H1; the epilogue reads a group of 32 columns, applies
+//     tanh(. + b1'), and writes the fp16 hi halves back into the first 16 columns of the group and the lo halves into
+//     the last 16.  The two accumulator stages are therefore used by layer 2 only, layer 1 of member m+1 never waits
+//     for an accumulator stage, and the MMA order alone (tcgen05.mma executes in issue order) guarantees that D1 of
+//     member m+1 overwrites H1 of member m only after layer 2 of member m has read it.
+//   * The epilogue is software-pipelined across members: E2(m, chunk 0) | E1(m+1) | E2(m, chunk 1).  H1 of the next
+//     member is produced as soon as the tensor pipe has finished with the current one, so the tensor pipe idles for
+//     half an E1 per member instead of E2(chunk 1) + half an E1.
+//   * tanh = 1 - 2/(1 + 2^(2x log2 e)) with ONE reciprocal per four activations (1/a from 1/(abcd) and the partial
+//     products, all on the FMA pipe): 1.25 MUFU per activation instead of 2.  The exponent is clamped at 30
+//     (tanh = 1 to fp32 precision beyond that) so that the product of four (1 + e) stays finite.
+//   * theta of the layer-2 tile a generator slot needs is staged by TMA: one thread issues one
+//     cp.async.bulk.tensor.2d (64 x 64 fp32 box of W2) per slot into a two-stage buffer, completion on an mbarrier;
+//     the generator threads read their 32 bytes from shared memory.  (Round 1 used two per-thread cp.async per slot.)
+//   * b2', W3', b3' of a member are generated AFTER its weight tiles (they are needed last), b1' before.
+//
+// Warp roles: warps 0-7 epilogue (two per TMEM lane quadrant, alternating 32-column groups), warps 8-23 weight
+// generators, warp 24 TMEM allocator + MMA issuer (leader CTA) / barrier relay lanes (follower CTA).
+#include <cuda.h>
+#include <stdlib.h>
+#include "des_common.cuh"
+#include "des_tc.cuh"
+
+namespace des {
+
+using namespace tc;
+
+namespace pairk {
+
+constexpr int kGenWarps = 16;
+constexpr int kGenThreads = kGenWarps * 32;
+constexpr int kEpiWarps = 8;
+constexpr int kMmaWarp = kEpiWarps + kGenWarps;
+constexpr int kThreads = (kEpiWarps + kGenWarps + 1) * 32;
+constexpr int kK1 = 32;                       // layer-1 K (state_dim zero-padded): 2 k-steps of 16
+constexpr int kMaxA = 8;
+constexpr int kNC = 128;                      // accumulator chunk = MMA N of the pair (64 rows of B per CTA)
+constexpr int kThetaStage = 64 * 64 * 4;      // one TMA box of W2: 64 rows x 64 columns fp32
+// Register budget: the kernel is launched with kLaunchRegs per thread (__maxnreg__), i.e. a pool of 800 x 72 = 57 600;
+// setmaxnreg then moves registers from the generators to the epilogue warps.  The sum must fit the pool, or the
+// epilogue's setmaxnreg.inc never returns.
+#ifndef DES_PAIR_GEN_REGS
+#define DES_PAIR_GEN_REGS 56
+#endif
+#ifndef DES_PAIR_EPI_REGS
+#define DES_PAIR_EPI_REGS 104
+#endif
+#ifndef DES_PAIR_MMA_REGS
+#define DES_PAIR_MMA_REGS 64
+#endif
+constexpr int kLaunchRegs = 72;     // 25 warps are allocated as 28 (granularity 4): 28 x 32 x 72 <= 65 536
+constexpr int kGenRegs = DES_PAIR_GEN_REGS, kEpiRegs = DES_PAIR_EPI_REGS, kMmaRegs = DES_PAIR_MMA_REGS;
+static_assert(kGenWarps * 32 * kGenRegs + kEpiWarps * 32 * kEpiRegs + 32 * kMmaRegs <= kThreads * kLaunchRegs,
+              "setmaxnreg budget exceeds the registers the CTA is launched with");
+
+template <int H, bool X3>
+struct Cfg {
+    static constexpr int NCH = H / kNC;                          // output-feature chunks per layer
+    static constexpr int KAT = H / 64;                           // 64-wide k atoms of layer 2
+    static constexpr int SLOT_BYTES = (X3 ? 2 : 1) * 64 * 128;   // this CTA's B tile: 64 rows x 128 B (hi [+ lo])
+    static constexpr int X_TILE_BYTES = (X3 ? 2 : 1) * 128 * 128;
+    static constexpr int SLOTS_PER_MEMBER = NCH + NCH * KAT;
+    static constexpr int ACC_BASE = H;                            // TMEM: [0,H) D1/H1, then two 128-column stages
+};
+
+struct Args {
+    float *fitness;
+    const float *theta, *obs, *target;
+    const des_state *state;
+    Layout L;
+    int n_slots, a4;            // a4 = action rows kept in shared memory (4 or 8)
+    float sigma, clip, neg2ln2_sigma2;
+    PhiloxKey key;
+    uint32_t gen;
+    uint64_t member_offset;
+    int64_t n_local;
+};
+
+struct Bars {
+    uint64_t slot_full[16], slot_empty[16];
+    uint64_t th_full[2], th_empty[2];
+    uint64_t s1_full[2], s1_empty[2], s2_full[2], s2_empty[2];
+    uint64_t d1_full[2], h_ready[2], acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+    float fit_part[2][4];
+};
+
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    uint64_t rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(pk2(a)), "l"(pk2(b)));
+    return upk2(rd);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA: one 2-D box of the tensor map into this CTA's shared memory, completion (bytes) on the mbarrier
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+// tanh(v + b) for four activations, biases pre-scaled by 2 log2(e): e = 2^min(v c + b c, 30), d = 1 + e,
+// 1/d_i from ONE reciprocal of d0 d1 d2 d3 and partial products; t = 1 - 2/d.   abs err ~3e-7.
+__device__ __forceinline__ void tanh4(float2 v01, float2 v23, float4 bs, float2 &t01, float2 &t23) {
+    const float2 c = make_float2(kTwoLog2e, kTwoLog2e);
+    float2 a01 = ffma2(v01, c, make_float2(bs.x, bs.y));
+    float2 a23 = ffma2(v23, c, make_float2(bs.z, bs.w));
+    a01.x = fminf(a01.x, 30.f); a01.y = fminf(a01.y, 30.f);
+    a23.x = fminf(a23.x, 30.f); a23.y = fminf(a23.y, 30.f);
+    float2 e01, e23;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e01.x) : "f"(a01.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e01.y) : "f"(a01.y));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e23.x) : "f"(a23.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e23.y) : "f"(a23.y));
+    const float2 one = make_float2(1.0f, 1.0f);
+    const float2 d01 = fadd2(e01, one), d23 = fadd2(e23, one);
+    const float2 p = fmul2(d01, d23);                   // (d0 d2, d1 d3)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p.x * p.y));
+    const float2 s = make_float2(r * p.y, r * p.x);     // (1/(d0 d2), 1/(d1 d3))
+    const float2 i01 = fmul2(s, d23);                   // (1/d0, 1/d1)
+    const float2 i23 = fmul2(s, d01);                   // (1/d2, 1/d3)
+    const float2 m2 = make_float2(-2.0f, -2.0f);
+    t01 = ffma2(m2, i01, one);
+    t23 = ffma2(m2, i23, one);
+}
+
+template <int REGS>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+
+template <bool X3>
+__device__ __forceinline__ void store_octet(uint8_t *slot, int r, int c8, const float (&w)[8]) {
+    uint4 hi, lo;
+    if (X3) {
+        split_h2(w[0], w[1], hi.x, lo.x); split_h2(w[2], w[3], hi.y, lo.y);
+        split_h2(w[4], w[5], hi.z, lo.z); split_h2(w[6], w[7], hi.w, lo.w);
+    } else {
+        hi.x = pack_h2(w[0], w[1]); hi.y = pack_h2(w[2], w[3]); hi.z = pack_h2(w[4], w[5]); hi.w = pack_h2(w[6], w[7]);
+    }
+    const int off = r * 128 + ((c8 ^ (r & 7)) << 4);          // SWIZZLE_128B
+    *reinterpret_cast<uint4 *>(slot + off) = hi;
+    if (X3) *reinterpret_cast<uint4 *>(slot + 8192 + off) = lo;
+}
+
+template <int H, bool X3>
+__global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_constant__ CUtensorMap w2_map) {
+    using C = Cfg<H, X3>;
+    const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *xs = smem;                                                    // X tile (hi [, lo])
+    uint8_t *ring = xs + C::X_TILE_BYTES;                                  // n_slots * SLOT_BYTES
+    uint8_t *th_stage = ring + (size_t)a.n_slots * C::SLOT_BYTES;          // 2 x 16 KB TMA destinations
+    float *small1 = reinterpret_cast<float *>(th_stage + 2 * kThetaStage); // [2][H]: b1' * 2log2e
+    const int s2_floats = H + a.a4 * H + kMaxA;                            // b2' * 2log2e | W3' [a4][H] | b3'[8]
+    float *small2 = small1 + 2 * H;                                        // [2][s2_floats]
+    Bars *bars = reinterpret_cast<Bars *>((reinterpret_cast<uintptr_t>(small2 + 2 * s2_floats) + 15) & ~(uintptr_t)15);
+    // action partial sums handed from the odd-group warp to the even-group warp of a quadrant: [2][128 rows][a4]
+    float *act_x = reinterpret_cast<float *>(bars + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Layout L = a.L;
+    const uint32_t gen = a.state ? (uint32_t)a.state->generation : a.gen;
+
+    if (warp == kMmaWarp) {
+        if (lane == 0) {
+            const uint32_t relay = rank == 0 ? 1u : 0u;      // the leader's copies also collect the follower's relay
+            for (int s = 0; s < a.n_slots; ++s) {
+                mbar_init(smem_u32(&bars->slot_full[s]), kGenWarps + relay);
+                mbar_init(smem_u32(&bars->slot_empty[s]), 1);
+            }
+            for (int p = 0; p < 2; ++p) {
+                mbar_init(smem_u32(&bars->th_full[p]), 1);
+                mbar_init(smem_u32(&bars->th_empty[p]), kGenWarps);
+                mbar_init(smem_u32(&bars->s1_full[p]), kGenWarps);
+                mbar_init(smem_u32(&bars->s1_empty[p]), kEpiWarps);
+                mbar_init(smem_u32(&bars->s2_full[p]), kGenWarps);
+                mbar_init(smem_u32(&bars->s2_empty[p]), kEpiWarps);
+                mbar_init(smem_u32(&bars->d1_full[p]), 1);
+                mbar_init(smem_u32(&bars->h_ready[p]), kEpiWarps + relay);
+                mbar_init(smem_u32(&bars->acc_full[p]), 1);
+                mbar_init(smem_u32(&bars->acc_empty[p]), kEpiWarps + relay);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc2(smem_u32(&bars->tmem_base), 512);
+    }
+    // X -> shared memory once: this CTA's 128 observations as fp16 (hi [, lo]) K-major SWIZZLE_128B, k < d0 (<= 32)
+    for (int idx = threadIdx.x; idx < 128 * 4; idx += blockDim.x) {
+        const int c8 = idx & 3, r = idx >> 2;
+        const float *orow = a.obs + (int64_t)((int)rank * 128 + r) * L.d0;
+        float w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w[e] = (c8 * 8 + e < L.d0) ? __ldg(orow + c8 * 8 + e) : 0.f;
+        uint4 hi, lo;
+        if (X3) {
+            split_h2(w[0], w[1], hi.x, lo.x); split_h2(w[2], w[3], hi.y, lo.y);
+            split_h2(w[4], w[5], hi.z, lo.z); split_h2(w[6], w[7], hi.w, lo.w);
+        } else {
+            hi.x = pack_h2(w[0], w[1]); hi.y = pack_h2(w[2], w[3]); hi.z = pack_h2(w[4], w[5]); hi.w = pack_h2(w[6], w[7]);
+        }
+        const int off = r * 128 + ((c8 ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4 *>(xs + off) = hi;
+        if (X3) *reinterpret_cast<uint4 *>(xs + 16384 + off) = lo;
+    }
+    // unused action rows of W3' stay zero (finite) in both buffers
+    for (int i = threadIdx.x; i < 2 * s2_floats; i += blockDim.x) small2[i] = 0.f;
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // the peer's barriers are initialised before anyone arrives on them
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    const int64_t first = blockIdx.x / 2;
+    const int64_t stride = gridDim.x / 2;
+    const int64_t n_mine = a.n_local > first ? (a.n_local - first + stride - 1) / stride : 0;
+
+    if (warp == kMmaWarp) {
+        reg_dealloc<kMmaRegs>();
+        if (lane == 0 && rank == 0) {
+            // =================================== MMA issuer (one thread of the leader) ===================================
+            constexpr uint32_t idesc = idesc_f16(256, kNC);
+            uint32_t rs = 0, rph = 0;            // ring cursor: slot index and phase
+            uint32_t acc_u = 0;                  // accumulator-stage use counter
+            const uint32_t xaddr = smem_u32(xs);
+            for (int64_t i = 0; i < n_mine; ++i) {
+                // ---- layer 1: D1 chunk nc = X W1'[128nc:128nc+128, :]^T, into the H1 columns (in-order after layer 2 of
+                //      the previous member, which read them)
+                for (int nc = 0; nc < C::NCH; ++nc) {
+                    const uint32_t s = rs, sph = rph;
+                    if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
+                    mbar_wait(smem_u32(&bars->slot_full[s]), sph);
+                    tc_fence_after();
+                    const uint32_t bbase = smem_u32(ring + (size_t)s * C::SLOT_BYTES);
+                    const uint32_t d = tmem + (uint32_t)(nc * kNC);
+#pragma unroll
+                    for (int ks = 0; ks < kK1 / 16; ++ks) {
+                        const uint64_t ah = smem_desc_sw128(xaddr) + (uint64_t)(ks * 2);
+                        const uint64_t bh = smem_desc_sw128(bbase) + (uint64_t)(ks * 2);
+                        mma2_f16_ss(d, ah, bh, idesc, ks > 0);
+                        if (X3) {
+                            const uint64_t al = smem_desc_sw128(xaddr + 16384) + (uint64_t)(ks * 2);
+                            const uint64_t bl = smem_desc_sw128(bbase + 8192) + (uint64_t)(ks * 2);
+                            mma2_f16_ss(d, al, bh, idesc, 1);       // X_lo W_hi
+                            mma2_f16_ss(d, ah, bl, idesc, 1);       // X_hi W_lo
+                        }
+                    }
+                    mma2_commit(smem_u32(&bars->slot_empty[s]));
+                    mma2_commit(smem_u32(&bars->d1_full[nc]));
+                }
+                // ---- layer 2: D2 chunk nc = H1 W2'[128nc:128nc+128, :]^T, k in atoms of 64
+                for (int nc = 0; nc < C::NCH; ++nc) {
+                    const uint32_t u = acc_u++, st = u & 1, ph = (u >> 1) & 1;
+                    mbar_wait(smem_u32(&bars->acc_empty[st]), ph ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem + (uint32_t)(C::ACC_BASE + st * kNC);
+                    for (int ka = 0; ka < C::KAT; ++ka) {
+                        const uint32_t s = rs, sph = rph;
+                        if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
+                        if (nc == 0 && (ka & 1) == 0) mbar_wait(smem_u32(&bars->h_ready[ka >> 1]), (uint32_t)i & 1);
+                        mbar_wait(smem_u32(&bars->slot_full[s]), sph);
+                        tc_fence_after();
+                        const uint32_t bbase = smem_u32(ring + (size_t)s * C::SLOT_BYTES);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            // H1 features 64ka + 16ks .. +16: group g = 2ka + ks/2, hi at column 32g + 8(ks%2), lo 16 further
+                            const uint32_t ah = tmem + (uint32_t)(32 * (2 * ka + (ks >> 1)) + 8 * (ks & 1));
+                            const uint64_t bh = smem_desc_sw128(bbase) + (uint64_t)(ks * 2);
+                            mma2_f16_ts(d, ah, bh, idesc, (ka | ks) != 0);
+                            if (X3) {
+                                const uint64_t bl = smem_desc_sw128(bbase + 8192) + (uint64_t)(ks * 2);
+                                mma2_f16_ts(d, ah + 16, bh, idesc, 1);      // H1_lo W_hi
+                                mma2_f16_ts(d, ah, bl, idesc, 1);           // H1_hi W_lo
+                            }
+                        }
+                        mma2_commit(smem_u32(&bars->slot_empty[s]));
+                    }
+                    mma2_commit(smem_u32(&bars->acc_full[st]));
+                }
+            }
+        }
+        if (rank == 1 && lane < 3) {
+            // ---- follower CTA: relay completed local phases to the leader's barriers, in the leader's wait order
+            if (lane == 0) {                      // slot_full: one relay per ring slot
+                uint32_t rs = 0, rph = 0;
+                for (int64_t i = 0; i < n_mine * C::SLOTS_PER_MEMBER; ++i) {
+                    mbar_wait(smem_u32(&bars->slot_full[rs]), rph);
+                    mbar_arrive_cluster(smem_u32(&bars->slot_full[rs]), 0);
+                    if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
+                }
+            } else if (lane == 1) {               // acc_empty: one relay per accumulator-stage use
+                for (int64_t u = 0; u < n_mine * C::NCH; ++u) {
+                    const uint32_t st = (uint32_t)u & 1, ph = (uint32_t)(u >> 1) & 1;
+                    mbar_wait(smem_u32(&bars->acc_empty[st]), ph);
+                    mbar_arrive_cluster(smem_u32(&bars->acc_empty[st]), 0);
+                }
+            } else {                              // h_ready: one relay per (member, chunk)
+                for (int64_t v = 0; v < n_mine; ++v) {
+                    for (int nc = 0; nc < C::NCH; ++nc) {
+                        mbar_wait(smem_u32(&bars->h_ready[nc]), (uint32_t)v & 1);
+                        mbar_arrive_cluster(smem_u32(&bars->h_ready[nc]), 0);
+                    }
+                }
+            }
+        }
+    } else if (warp < kEpiWarps) {
+        // =================================== epilogue warps ============================================
+        reg_alloc<kEpiRegs>();
+        const int par = warp >> 2;                                    // this warp owns the 32-column groups g with (g & 1) == par
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
+        const int row = (warp & 3) * 32 + lane;                       // observation row inside this CTA's tile
+        const uint32_t tbase = tmem + lane_off;
+        const uint32_t s1_addr = smem_u32(small1), s2_addr = smem_u32(small2);
+        uint32_t acc_u = 0;
+
+        // ---------------- E1: H1 = tanh(D1 + b1') -> fp16 (hi [, lo]) written back IN PLACE
+        auto epilogue1 = [&](uint32_t mi) {
+            const uint32_t p = mi & 1;
+            mbar_wait(smem_u32(&bars->s1_full[p]), (mi >> 1) & 1);
+            const uint32_t b1 = s1_addr + p * (H * 4);
+            for (int nc = 0; nc < C::NCH; ++nc) {
+                mbar_wait(smem_u32(&bars->d1_full[nc]), mi & 1);
+                tc_fence_after();
+                uint32_t va[16], vb[16];
+                tmem_ld16(tbase + 32 * (nc * 4 + par), va);
+                tmem_ld16(tbase + 32 * (nc * 4 + par) + 16, vb);
+#pragma unroll
+                for (int gi = 0; gi < 2; ++gi) {
+                    const int g = nc * 4 + gi * 2 + par;                  // 32-column group
+                    tmem_wait_ld16(va);                                   // both halves of the group are in registers:
+                    tmem_wait_ld16(vb);                                   // its columns may be overwritten
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t *v = hf ? vb : va;
+                            const float4 b = lds128(b1 + (32 * g + 16 * hf + 4 * i) * 4);
+                            const float2 v01 = make_float2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]));
+                            const float2 v23 = make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                            if (X3) {
+                                float2 t01, t23;
+                                tanh4(v01, v23, b, t01, t23);
+                                split_h2p(t01, hi[8 * hf + 2 * i], lo[8 * hf + 2 * i]);
+                                split_h2p(t23, hi[8 * hf + 2 * i + 1], lo[8 * hf + 2 * i + 1]);
+                            } else {
+                                const float2 x01 = fadd2(v01, make_float2(b.x, b.y)), x23 = fadd2(v23, make_float2(b.z, b.w));
+                                hi[8 * hf + 2 * i] = pack_h2(tanh_fast(x01.x), tanh_fast(x01.y));
+                                hi[8 * hf + 2 * i + 1] = pack_h2(tanh_fast(x23.x), tanh_fast(x23.y));
+                            }
+                        }
+                        // the next group of this chunk (other columns) streams in while this one is computed
+                        if (gi == 0) tmem_ld16(tbase + 32 * (g + 2) + 16 * hf, hf ? vb : va);
+                    }
+                    tmem_st16(tbase + 32 * g, hi);
+                    if (X3) tmem_st16(tbase + 32 * g + 16, lo);
+                }
+                tmem_wait_st();                       // this chunk of H1 is complete: its k-atoms may be consumed
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars->h_ready[nc]));
+            }
+            if (lane == 0) mbar_arrive(smem_u32(&bars->s1_empty[p]));
+        };
+
+        float2 actp[kMaxA];                          // (even-n, odd-n) partial sums of action q
+        // ---------------- E2 chunk nc: H2 = tanh(D2 + b2'); a += H2 W3'^T in fp32 registers
+        auto epilogue2 = [&](uint32_t p, int nc) {
+            const uint32_t u = acc_u++, st = u & 1, ph = (u >> 1) & 1;
+            const uint32_t b2 = s2_addr + p * (uint32_t)(s2_floats * 4);
+            const uint32_t w3 = b2 + H * 4;
+            mbar_wait(smem_u32(&bars->acc_full[st]), ph);
+            tc_fence_after();
+            const uint32_t acc_base = tbase + (uint32_t)(C::ACC_BASE + st * kNC);
+            uint32_t va[16], vb[16];
+            tmem_ld16(acc_base + 32 * par, va);
+            tmem_ld16(acc_base + 32 * par + 16, vb);
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi) {
+                const int gcol = 32 * (gi * 2 + par);                     // column of this group inside the chunk
+                tmem_wait_ld16(va);
+                tmem_wait_ld16(vb);
+                if (gi == 1) {                                 // every load of this accumulator stage has landed
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[st]));
+                }
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t *v = hf ? vb : va;
+                        const int n0 = nc * kNC + gcol + 16 * hf + 4 * i;
+                        const float4 b = lds128(b2 + n0 * 4);
+                        const float2 v01 = make_float2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]));
+                        const float2 v23 = make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                        float2 h01, h23;
+                        if (X3) {
+                            tanh4(v01, v23, b, h01, h23);
+                        } else {
+                            const float2 x01 = fadd2(v01, make_float2(b.x, b.y)), x23 = fadd2(v23, make_float2(b.z, b.w));
+                            h01 = make_float2(tanh_fast(x01.x), tanh_fast(x01.y));
+                            h23 = make_float2(tanh_fast(x23.x), tanh_fast(x23.y));
+                        }
+                        // layer 3 (model.py:38) in fp32 on packed FFMA2: W3' row-major [q][n], 4 consecutive n per LDS.128
+#pragma unroll
+                        for (int q = 0; q < kMaxA; ++q) {
+                            if (q < 4 || a.a4 > 4) {
+                                const float4 w = lds128(w3 + (q * H + n0) * 4);
+                                actp[q] = ffma2(h01, make_float2(w.x, w.y), actp[q]);
+                                actp[q] = ffma2(h23, make_float2(w.z, w.w), actp[q]);
+                            }
+                        }
+                    }
+                    if (gi == 0) tmem_ld16(acc_base + 32 * (2 + par) + 16 * hf, hf ? vb : va);     // next group
+                }
+            }
+        };
+
+        uint32_t mi = 0;
+        if (n_mine > 0) epilogue1(0);
+        for (int64_t i = 0; i < n_mine; ++i, ++mi) {
+            const int64_t m = first + i * stride;
+            const uint32_t p = mi & 1;
+            mbar_wait(smem_u32(&bars->s2_full[p]), (mi >> 1) & 1);
+#pragma unroll
+            for (int q = 0; q < kMaxA; ++q) actp[q] = make_float2(0.f, 0.f);
+            for (int nc = 0; nc < C::NCH - 1; ++nc) epilogue2(p, nc);
+            if (i + 1 < n_mine) epilogue1(mi + 1);              // the next member's H1, ahead of this member's last chunk
+            epilogue2(p, C::NCH - 1);
+            // ---- member done: combine the two warps of the quadrant, clip, squared error (utils.py:134-137)
+            float act[kMaxA];
+#pragma unroll
+            for (int q = 0; q < kMaxA; ++q) act[q] = actp[q].x + actp[q].y;
+            float sq = 0.f;
+            if (par == 1) {
+#pragma unroll
+                for (int q = 0; q < kMaxA; ++q)
+                    if (q < a.a4) act_x[(p * 128 + row) * a.a4 + q] = act[q];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars->s2_empty[p]));     // done with this member's b2/W3
+                asm volatile("bar.arrive %0, 256;" ::"r"(2 + p) : "memory");     // ids alternate with the member parity
+            } else {
+                asm volatile("bar.sync %0, 256;" ::"r"(2 + p) : "memory");
+                const uint32_t b3 = s2_addr + p * (uint32_t)(s2_floats * 4) + (uint32_t)((H + a.a4 * H) * 4);
+                const int t = (int)rank * 128 + row;
+#pragma unroll
+                for (int q = 0; q < kMaxA; ++q) {
+                    if (q < L.A) {
+                        float v = (act[q] + act_x[(p * 128 + row) * a.a4 + q]) + lds32(b3 + q * 4);     // fixed order: even + odd groups
+                        v = fminf(fmaxf(v, -a.clip), a.clip);
+                        const float d = v - __ldg(a.target + (int64_t)t * L.A + q);
+                        sq = __fmaf_rn(d, d, sq);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                if (lane == 0) {
+                    bars->fit_part[p][warp] = sq;
+                    mbar_arrive(smem_u32(&bars->s2_empty[p]));
+                }
+                if (warp == 0) {
+                    asm volatile("bar.sync %0, 128;" ::"r"(4 + p) : "memory");
+                    if (lane == 0) {
+                        double f = 0.0;
+                        for (int w = 0; w < 4; ++w) f += (double)bars->fit_part[p][w];
+                        // the pair adds its two halves into the (pre-zeroed) output: two commutative fp32 adds -> deterministic
+                        atomicAdd(a.fitness + m, (float)(-f));
+                    }
+                } else {
+                    asm volatile("bar.arrive %0, 128;" ::"r"(4 + p) : "memory");
+                }
+            }
+        }
+    } else {
+        // =================================== weight generators =========================================
+        reg_dealloc<kGenRegs>();
+        const int gtid = threadIdx.x - kEpiWarps * 32;                  // 0..511
+        uint32_t rs = 0, rph = 0;                                       // ring cursor: slot index and phase
+        const int r2 = gtid >> 3, c82 = gtid & 7;
+        const int row_base = 64 * (int)rank;                            // this CTA's 64 rows of every 128-row chunk
+        // theta of a layer-2 tile does not depend on the member: TMA stages the 64 x 64 fp32 box one slot ahead
+        uint32_t tq = 0;                                                // layer-2 slots generated so far (stage = tq & 1)
+        const int64_t tq_total = n_mine * (C::NCH * C::KAT);
+        auto theta_issue = [&](uint32_t q) {                            // gtid == 0 only
+            const uint32_t stg = q & 1;
+            const int w = (int)(q % (uint32_t)(C::NCH * C::KAT));
+            const int nc = w / C::KAT, ka = w % C::KAT;
+            const uint32_t bar = smem_u32(&bars->th_full[stg]);
+            mbar_expect_tx(bar, kThetaStage);
+            tma_load_2d(smem_u32(th_stage + stg * kThetaStage), &w2_map, ka * 64, nc * kNC + row_base, bar);
+        };
+        if (gtid == 0) {
+            if (tq_total > 0) theta_issue(0);
+            if (tq_total > 1) theta_issue(1);
+        }
+        const float bsc = X3 ? kTwoLog2e : 1.0f;     // the f16x3 epilogue evaluates tanh(v + b) as 1 - 2/(1 + 2^(v c + b c))
+        uint32_t mi = 0;
+        for (int64_t i = 0; i < n_mine; ++i, ++mi) {
+            const uint32_t member = (uint32_t)(a.member_offset + (uint64_t)(first + i * stride));
+            const uint32_t p = mi & 1;
+            // ---- b1' (needed first)
+            mbar_wait(smem_u32(&bars->s1_empty[p]), ((mi >> 1) & 1) ^ 1);
+            for (int k = gtid; k < H / 4; k += kGenThreads) {
+                const float4 v1 = perturbed_quad((uint32_t)((L.off_b1 >> 2) + k), member, gen, kStreamNesEps, a.key,
+                                                 a.neg2ln2_sigma2, __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_b1) + k));
+                reinterpret_cast<float4 *>(small1 + p * H)[k] = make_float4(v1.x * bsc, v1.y * bsc, v1.z * bsc, v1.w * bsc);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->s1_full[p]));
+            // ---- layer-1 tiles: rows [128nc + 64 rank, +64) of W1', k < d0 (zero padded to 32)
+            for (int nc = 0; nc < C::NCH; ++nc) {
+                const uint32_t s = rs, sph = rph;
+                if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
+                mbar_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
+                uint8_t *slot = ring + (size_t)s * C::SLOT_BYTES;
+                if (gtid < 256) {   // 64 rows x 4 octets = 256 items
+                    const int r = gtid >> 2, c8 = gtid & 3;
+                    const int n = nc * kNC + row_base + r;
+                    float w[8];
+                    if ((L.d0 & 3) == 0) {                                // row starts are quad aligned
+#pragma unroll
+                        for (int hq = 0; hq < 2; ++hq) {
+                            const int k = c8 * 8 + hq * 4;
+                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (k < L.d0) {
+                                const int j = L.off_w1 + n * L.d0 + k;
+                                v = perturbed_quad((uint32_t)(j >> 2), member, gen, kStreamNesEps, a.key, a.neg2ln2_sigma2,
+                                                   __ldg(reinterpret_cast<const float4 *>(a.theta + j)));
+                            }
+                            w[4 * hq] = v.x; w[4 * hq + 1] = v.y; w[4 * hq + 2] = v.z; w[4 * hq + 3] = v.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int k = c8 * 8 + e;
+                            float x = 0.f;
+                            if (k < L.d0) {
+                                const int j = L.off_w1 + n * L.d0 + k;
+                                const float4 z = noise_quad((uint32_t)(j >> 2), member, gen, kStreamNesEps, a.key);
+                                const int el = j & 3;
+                                const float zz = el == 0 ? z.x : (el == 1 ? z.y : (el == 2 ? z.z : z.w));
+                                x = __fmaf_rn(a.sigma, zz, __ldg(a.theta + j));
+                            }
+                            w[e] = x;
+                        }
+                    }
+                    store_octet<X3>(slot, r, c8, w);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars->slot_full[s]));
+            }
+            // ---- layer-2 tiles: rows [128nc + 64 rank, +64) x k [64ka, +64) of W2': one octet per thread
+            for (int nc = 0; nc < C::NCH; ++nc) {
+                for (int ka = 0; ka < C::KAT; ++ka) {
+                    const uint32_t s = rs, sph = rph;
+                    if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
+                    const uint32_t stg = tq & 1, tph = (tq >> 1) & 1;
+                    if (gtid == 0 && tq >= 1 && (int64_t)tq + 1 < tq_total) {
+                        // the stage slot tq-1 used has been read by all sixteen warps: refill it with the box of slot tq+1
+                        mbar_wait(smem_u32(&bars->th_empty[stg ^ 1]), ((tq - 1) >> 1) & 1);
+                        theta_issue(tq + 1);
+                    }
+                    ++tq;
+                    const int j0 = L.off_w2 + (nc * kNC + row_base + r2) * H + ka * 64 + c82 * 8;
+                    const uint4 x0 = philox4x32((uint32_t)(j0 >> 2), member, gen, kStreamNesEps, a.key);
+                    const uint4 x1 = philox4x32((uint32_t)(j0 >> 2) + 1, member, gen, kStreamNesEps, a.key);
+                    const BmParts pa = box_muller_parts(x0.x, x0.y, a.neg2ln2_sigma2);
+                    const BmParts pb = box_muller_parts(x0.z, x0.w, a.neg2ln2_sigma2);
+                    const BmParts pc = box_muller_parts(x1.x, x1.y, a.neg2ln2_sigma2);
+                    const BmParts pd = box_muller_parts(x1.z, x1.w, a.neg2ln2_sigma2);
+                    mbar_wait(smem_u32(&bars->th_full[stg]), tph);           // this slot's theta box has landed
+                    const uint32_t cell = smem_u32(th_stage + stg * kThetaStage) + (uint32_t)(r2 * 256 + c82 * 32);
+                    const float4 t0 = lds128(cell), t1 = lds128(cell + 16);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bars->th_empty[stg]));
+                    const float w[8] = {__fmaf_rn(pa.nr, pa.c, t0.x), __fmaf_rn(pa.nr, pa.s, t0.y),
+                                        __fmaf_rn(pb.nr, pb.c, t0.z), __fmaf_rn(pb.nr, pb.s, t0.w),
+                                        __fmaf_rn(pc.nr, pc.c, t1.x), __fmaf_rn(pc.nr, pc.s, t1.y),
+                                        __fmaf_rn(pd.nr, pd.c, t1.z), __fmaf_rn(pd.nr, pd.s, t1.w)};
+                    mbar_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
+                    store_octet<X3>(ring + (size_t)s * C::SLOT_BYTES, r2, c82, w);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bars->slot_full[s]));
+                }
+            }
+            // ---- b2', W3', b3' (needed last: the epilogue of layer 2)
+            mbar_wait(smem_u32(&bars->s2_empty[p]), ((mi >> 1) & 1) ^ 1);
+            float *sm2 = small2 + p * s2_floats;
+            for (int k = gtid; k < H / 4; k += kGenThreads) {
+                const float4 v2 = perturbed_quad((uint32_t)((L.off_b2 >> 2) + k), member, gen, kStreamNesEps, a.key,
+                                                 a.neg2ln2_sigma2, __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_b2) + k));
+                reinterpret_cast<float4 *>(sm2)[k] = make_float4(v2.x * bsc, v2.y * bsc, v2.z * bsc, v2.w * bsc);
+            }
+            for (int k = gtid; k < L.A * H / 4; k += kGenThreads)            // W3' [q][n] row-major: aligned quads
+                reinterpret_cast<float4 *>(sm2 + H)[k] =
+                    perturbed_quad((uint32_t)((L.off_w3 >> 2) + k), member, gen, kStreamNesEps, a.key, a.neg2ln2_sigma2,
+                                   __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_w3) + k));
+            if (gtid < L.A) {
+                const int j = L.off_b3 + gtid;
+                const float4 z = noise_quad((uint32_t)(j >> 2), member, gen, kStreamNesEps, a.key);
+                const int el = j & 3;
+                const float zz = el == 0 ? z.x : (el == 1 ? z.y : (el == 2 ? z.z : z.w));
+                sm2[H + a.a4 * H + gtid] = __fmaf_rn(a.sigma, zz, __ldg(a.theta + j));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->s2_full[p]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // no CTA leaves (or frees TMEM) while its peer may still signal or read it
+    if (warp == kMmaWarp) tmem_dealloc2(tmem, 512);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+template <int H, bool X3>
+static int launch(Args &a, cudaStream_t st) {
+    using C = Cfg<H, X3>;
+    // tensor map of fc2.weight: [H rows][H columns] fp32 inside theta, boxes of 64 x 64
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) {
+        set_error("des_nes_eval(tensor): cuTensorMapEncodeTiled is not available from this driver");
+        return DES_ERR_UNSUPPORTED;
+    }
+    CUtensorMap map;
+    const cuuint64_t gdim[2] = {(cuuint64_t)H, (cuuint64_t)H};
+    const cuuint64_t gstride[1] = {(cuuint64_t)H * sizeof(float)};
+    const cuuint32_t box[2] = {64, 64};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)(a.theta + a.L.off_w2), gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("des_nes_eval(tensor): cuTensorMapEncodeTiled failed (%d)", (int)cr);
+        return DES_ERR_CUDA;
+    }
+    a.a4 = a.L.A > 4 ? 8 : 4;
+    const size_t s2_floats = (size_t)H + (size_t)a.a4 * H + kMaxA;
+    const size_t fixed = 1024 + C::X_TILE_BYTES + 2 * kThetaStage + (2 * H + 2 * s2_floats) * sizeof(float) + 16 + sizeof(Bars) +
+                         2 * 128 * (size_t)a.a4 * sizeof(float);
+    int n_slots = (int)((227 * 1024 - fixed) / C::SLOT_BYTES);
+    if (n_slots > 16) n_slots = 16;
+    if (n_slots < 4) {
+        set_error("des_nes_eval(tensor): no shared memory left for the weight ring (H=%d)", H);
+        return DES_ERR_UNSUPPORTED;
+    }
+    a.n_slots = n_slots;
+    const size_t smem = fixed + (size_t)n_slots * C::SLOT_BYTES;
+    int dev = 0, sms = 148;
+    DES_CUDA(cudaGetDevice(&dev));
+    DES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    DES_CUDA(cudaFuncSetAttribute(eval_pair_kernel<H, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // each pair accumulates its two halves into the output with atomicAdd: zero it first
+    DES_CUDA(cudaMemsetAsync(a.fitness, 0, (size_t)a.n_local * sizeof(float), st));
+    const int64_t pairs = a.n_local < sms / 2 ? a.n_local : sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DES_CUDA(cudaLaunchKernelEx(&cfg, eval_pair_kernel<H, X3>, a, map));
+    DES_LAUNCH_CHECK("eval_pair_kernel");
+    return DES_OK;
+}
+
+}  // namespace pairk
+
+// Shapes the pair pipeline covers; everything else runs on eval_tc_kernel (des_eval_tc.cu).
+bool eval_pair_supported(des_dims dims, int precision) {
+    const char *e = getenv("DES_TC_PAIR_V2");
+    if (e && e[0] == '0') return false;
+    return precision == DES_FWD_F16X3 && (dims.hidden == 128 || dims.hidden == 256) && dims.tape_len == 256 &&
+           dims.state_dim <= pairk::kK1 && dims.action_dim <= pairk::kMaxA;
+}
+
+int eval_pair_launch(float *fitness, const float *theta, const float *obs, const float *target, des_dims dims, double sigma,
+                     double clip, uint64_t seed, uint64_t generation, const des_state *state, int64_t member_offset,
+                     int64_t n_local, int precision, cudaStream_t st) {
+    using namespace pairk;
+    if (((uintptr_t)theta & 15) != 0) {
+        set_error("des_nes_eval(tensor): theta_dev must be 16-byte aligned");
+        return DES_ERR_INVALID_ARGUMENT;
+    }
+    Args a;
+    a.fitness = fitness; a.theta = theta; a.obs = obs; a.target = target; a.state = state;
+    a.L = Layout(dims.state_dim, dims.hidden, dims.action_dim);
+    a.sigma = (float)sigma; a.clip = (float)clip;
+    a.neg2ln2_sigma2 = kNeg2Ln2 * (float)sigma * (float)sigma;
+    a.key = make_philox_key(seed); a.gen = (uint32_t)generation;
+    a.member_offset = (uint64_t)member_offset; a.n_local = n_local;
+    (void)precision;
+    return dims.hidden == 256 ? launch<256, true>(a, st) : launch<128, true>(a, st);
+}
+
+}  // namespace des

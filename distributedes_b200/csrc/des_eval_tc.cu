@@ -657,8 +657,8 @@ __global__ void __launch_bounds__((8 + kGenWarps + 1) * 32, 1) eval_tc_kernel(Tc
                                 t0 = __ldg(reinterpret_cast<const float4 *>(a.theta + j0));
                                 t1 = __ldg(reinterpret_cast<const float4 *>(a.theta + j0 + 4));
                             }
-                            const uint4 x0 = philox4x32_10((uint32_t)(j0 >> 2), member, gen, kStreamNesEps, a.key);
-                            const uint4 x1 = philox4x32_10((uint32_t)(j0 >> 2) + 1, member, gen, kStreamNesEps, a.key);
+                            const uint4 x0 = philox4x32((uint32_t)(j0 >> 2), member, gen, kStreamNesEps, a.key);
+                            const uint4 x1 = philox4x32((uint32_t)(j0 >> 2) + 1, member, gen, kStreamNesEps, a.key);
                             const BmParts pa = box_muller_parts(x0.x, x0.y, a.neg2ln2_sigma2);
                             const BmParts pb = box_muller_parts(x0.z, x0.w, a.neg2ln2_sigma2);
                             const BmParts pc = box_muller_parts(x1.x, x1.y, a.neg2ln2_sigma2);
@@ -793,11 +793,20 @@ size_t eval_tc_workspace_bytes(des_dims dims, int precision) {
     return (size_t)sms * spm * sb;
 }
 
+bool eval_pair_supported(des_dims dims, int precision);
+int eval_pair_launch(float *fitness, const float *theta, const float *obs, const float *target, des_dims dims, double sigma,
+                     double clip, uint64_t seed, uint64_t generation, const des_state *state, int64_t member_offset,
+                     int64_t n_local, int precision, cudaStream_t st);
+
 int eval_tc_launch(float *fitness, const float *theta, const float *obs, const float *target, des_dims dims,
                    double sigma, double clip, uint64_t seed, uint64_t generation, const des_state *state,
                    int64_t member_offset, int64_t n_local, int precision, void *workspace, size_t workspace_bytes,
                    cudaStream_t st) {
     const int H = dims.hidden;
+    // tape of 256 observations on CTA pairs: the pipelined pair kernel (des_eval_pair.cu)
+    if (pair_enabled() && eval_pair_supported(dims, precision))
+        return eval_pair_launch(fitness, theta, obs, target, dims, sigma, clip, seed, generation, state, member_offset,
+                                n_local, precision, st);
     if (!(H == 64 || H == 128 || H == 256) || dims.state_dim > kK1 || dims.action_dim > kMaxA || dims.tape_len % 128 != 0) {
         set_error("des_nes_eval(tensor): needs hidden in {64,128,256}, state_dim <= %d, action_dim <= %d, tape_len %% 128 == 0 "
                   "(got d0=%d H=%d A=%d T=%d); use DES_FWD_FP32 for other shapes", kK1, kMaxA, dims.state_dim, H,

@@ -7,7 +7,7 @@
 //
 // The reduction never reads eps from memory: every thread owns one quad of parameters (4 consecutive j)
 // and a contiguous slice of members, regenerates the quad's four normals per member from the counter
-// RNG and FMAs them with the member's shaped fitness.  Work = one Philox4x32-10 + two Box-Muller per
+// RNG and FMAs them with the member's shaped fitness.  Work = one Philox4x32-7 + two Box-Muller per
 // 4 products: the kernel is ALU/MUFU bound, HBM traffic is O(n_local + C*P).
 // Under the materialised-noise contract of SURVEY §8d it stands for reading 4*n_local*P bytes.
 #include "des_common.cuh"
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kGradThreads) grad_chunk_kernel(float *__restr
 #pragma unroll 2
     for (int64_t i = i0; i < i1; ++i) {
         const float s = __ldg(shaped + i);     // warp-uniform broadcast load
-        const uint4 x = philox4x32_10((uint32_t)q, (uint32_t)(member_offset + i), gen, kStreamNesEps, key);
+        const uint4 x = philox4x32((uint32_t)q, (uint32_t)(member_offset + i), gen, kStreamNesEps, key);
         const BmParts a = box_muller_parts(x.x, x.y, kNeg2Ln2);
         const BmParts b = box_muller_parts(x.z, x.w, kNeg2Ln2);
         const float as = a.nr * s, bs = b.nr * s;                 // s_i * radius: one multiply per pair

@@ -19,7 +19,7 @@
  *       [fc1.weight (H x d0 row-major) | fc1.bias (H) | fc2.weight (H x H) | fc2.bias (H)
  *        | fc3.weight (A x H) | fc3.bias (A)]
  *   - Noise contract: eps[member][j] is a pure function of (seed, generation, GLOBAL member index,
- *     j): Philox4x32-10, counter = (j/4, member, generation, stream_tag), key = (seed_lo, seed_hi);
+ *     j): Philox4x32-7 (Random123 constants, 7 rounds), counter = (j/4, member, generation, stream_tag), key = (seed_lo, seed_hi);
  *     words (x0,x1) -> Box-Muller -> (eps[4q], eps[4q+1]); (x2,x3) -> (eps[4q+2], eps[4q+3]).
  *     Box-Muller on the LOW 23 bits k of each word, f = 1 + k*2^-23:  u1 = f1 - (1 - 2^-24) in (0,1),
  *     ang = fl32(f2*fl32(2 pi) - fl32(3 pi - pi 2^-23)) ~ 2 pi u2 - pi,

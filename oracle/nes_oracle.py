@@ -15,14 +15,14 @@ against the reference's *own functions* imported from ``/root/reference`` by
 ``oracle/make_golden.py`` (fixtures committed under ``tests/golden/``) and checked by
 ``tests/test_oracle_golden.py``.  The counter-based RNG is ours (the reference seeds MT19937 from
 OS entropy, ``natural_es.py:23``, so it has no reproducible stream); it is pinned to the published
-Random123 Philox4x32-10 known-answer vectors.
+Random123 Philox4x32 known-answer vectors (the product uses 7 rounds).
 """
 from __future__ import annotations
 
 import numpy as np
 
 # --------------------------------------------------------------------------------------------
-# Counter-based noise:  Philox4x32-10  +  Box-Muller
+# Counter-based noise:  Philox4x32-7  +  Box-Muller
 # --------------------------------------------------------------------------------------------
 PHILOX_M0 = np.uint64(0xD2511F53)
 PHILOX_M1 = np.uint64(0xCD9E8D57)
@@ -35,8 +35,12 @@ STREAM_NES_EPS = 0  # counter word c3 for NES perturbations
 STREAM_CMA_Z = 1    # counter word c3 for CMA-ES z samples
 
 
-def philox4x32_10(c0, c1, c2, c3, k0, k1):
-    """Philox4x32 with 10 rounds (Salmon et al., SC'11; Random123 reference constants).
+PHILOX_ROUNDS = 7   # the noise contract (include/des_b200.h): Philox4x32-7, the smallest BigCrush-passing round count
+
+
+def philox4x32(c0, c1, c2, c3, k0, k1, rounds=PHILOX_ROUNDS):
+    """Philox4x32 with `rounds` rounds (Salmon et al., SC'11; Random123 reference constants).  The same loop is
+    pinned to the Random123 known-answer vectors at 7 and 10 rounds (tests/test_oracle_golden.py).
 
     All arguments broadcastable integer arrays holding uint32 values; returns four uint32 arrays.
     """
@@ -47,7 +51,7 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     k0 = int(k0) & 0xFFFFFFFF
     k1 = int(k1) & 0xFFFFFFFF
     c0, c1, c2, c3 = np.broadcast_arrays(c0, c1, c2, c3)
-    for _ in range(10):
+    for _ in range(rounds):
         p0 = PHILOX_M0 * c0            # < 2^64, exact in uint64
         p1 = PHILOX_M1 * c2
         n0 = (p1 >> _SH32) ^ c1 ^ np.uint64(k0)
@@ -86,7 +90,7 @@ def box_muller(xa, xb):
 def noise_uint32(seed, gen, member, n_quads, stream=STREAM_NES_EPS):
     """Raw Philox words for one member: counter = (quad, member, gen, stream), key = seed."""
     q = np.arange(n_quads, dtype=np.uint64)
-    return philox4x32_10(q, np.uint64(member), np.uint64(gen & 0xFFFFFFFF), np.uint64(stream),
+    return philox4x32(q, np.uint64(member), np.uint64(gen & 0xFFFFFFFF), np.uint64(stream),
                          seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
 
 
@@ -100,7 +104,7 @@ def noise(seed, gen, member_offset, n_members, P, stream=STREAM_NES_EPS):
     nq = (P + 3) // 4
     q = np.arange(nq, dtype=np.uint64)[None, :]
     m = (np.arange(n_members, dtype=np.uint64) + np.uint64(member_offset))[:, None]
-    x0, x1, x2, x3 = philox4x32_10(q, m, np.uint64(gen & 0xFFFFFFFF), np.uint64(stream),
+    x0, x1, x2, x3 = philox4x32(q, m, np.uint64(gen & 0xFFFFFFFF), np.uint64(stream),
                                    seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     z0, z1 = box_muller(x0, x1)
     z2, z3 = box_muller(x2, x3)

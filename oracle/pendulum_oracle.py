@@ -31,7 +31,7 @@ def reset_states(seed, gen, members, reps):
     members = np.asarray(members, dtype=np.uint64).reshape(-1, 1)
     r = np.arange(reps, dtype=np.uint64).reshape(1, -1)
     k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
-    x0, x1, _, _ = orc.philox4x32_10(r + 0 * members, members + 0 * r, np.uint64(gen & 0xFFFFFFFF),
+    x0, x1, _, _ = orc.philox4x32(r + 0 * members, members + 0 * r, np.uint64(gen & 0xFFFFFFFF),
                                       np.uint64(STREAM_ENV_RESET), k0, k1)
     u0 = ((x0 & np.uint64(0x7FFFFF)).astype(np.float64) + 0.5) / 8388608.0
     u1 = ((x1 & np.uint64(0x7FFFFF)).astype(np.float64) + 0.5) / 8388608.0
@@ -82,7 +82,7 @@ def rollouts(flat, H, seed, gen, members, reps, stats=None, horizon=HORIZON, cli
         if act_noise:
             k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
             ep = (members.reshape(-1, 1) * np.uint64(16) + np.arange(reps, dtype=np.uint64).reshape(1, -1)) & np.uint64(0xFFFFFFFF)
-            x0, x1, _, _ = orc.philox4x32_10(np.uint64(t) + 0 * ep, ep, np.uint64(gen & 0xFFFFFFFF),
+            x0, x1, _, _ = orc.philox4x32(np.uint64(t) + 0 * ep, ep, np.uint64(gen & 0xFFFFFFFF),
                                               np.uint64(STREAM_ACT_NOISE), k0, k1)
             z0, _ = orc.box_muller(x0, x1)
             act = act + z0 * act_noise

@@ -13,14 +13,20 @@ def load(golden_dir, name):
 
 
 def test_philox_known_answers():
-    # Random123 kat_vectors, philox4x32-10
-    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
-           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
-           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
-            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
-    for ctr, key, want in kat:
-        got = orc.philox4x32_10(*[np.asarray([c]) for c in ctr], *key)
-        assert tuple(int(g[0]) for g in got) == want
+    # Random123 kat_vectors: philox4x32 at 7 rounds (the noise contract, include/des_b200.h) and at 10 rounds
+    ctrs = [((0, 0, 0, 0), (0, 0)), ((0xffffffff,) * 4, (0xffffffff,) * 2),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0))]
+    kat = {7: [(0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48), (0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662),
+               (0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a)],
+           10: [(0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd),
+                (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)]}
+    assert orc.PHILOX_ROUNDS == 7
+    for rounds, wants in kat.items():
+        for (ctr, key), want in zip(ctrs, wants):
+            got = orc.philox4x32(*[np.asarray([c]) for c in ctr], *key, rounds=rounds)
+            assert tuple(int(g[0]) for g in got) == want
+    got = orc.philox4x32(*[np.asarray([c]) for c in ctrs[2][0]], *ctrs[2][1])        # the default is the contract
+    assert tuple(int(g[0]) for g in got) == kat[7][2]
 
 
 def test_noise_is_standard_normal_and_counter_based():
