@@ -129,6 +129,27 @@ def cpu_baseline_for(d0, H, A, T, pop, ref_pop=0, port_seconds=4.0):
     return out
 
 
+def cma_cpu_baseline(n, lam):
+    """fp64 numpy restatement of the rank-mu update (BLAS, all host threads): pycma is unavailable."""
+    try:
+        from oracle import cma_oracle as co
+        rs = np.random.RandomState(0)
+        Y = rs.randn(lam, n)
+        w = rs.rand(lam)
+        C = np.eye(n)
+        pc = rs.randn(n)
+        co.cov_update(C, co.rank_mu_delta(Y, w), pc, 0.001, 0.009, w.sum())
+        t0 = time.perf_counter()
+        reps = 3 if n <= 1024 else 1
+        for _ in range(reps):
+            co.cov_update(C, co.rank_mu_delta(Y, w), pc, 0.001, 0.009, w.sum())
+        sec = (time.perf_counter() - t0) / reps
+        return {'value': 1.0 / sec, 'unit': 'updates/s', 'cores': os.cpu_count(), 'kind': 'port',
+                'sample': 'fp64 numpy restatement (BLAS Y^T diag(w) Y + covariance update), %d repetition(s); pycma unavailable' % reps}
+    except Exception as e:
+        return {'value': None, 'unit': 'updates/s', 'cores': None, 'kind': 'port', 'sample': 'failed: %s' % str(e)[:200]}
+
+
 def run_reference(a):
     """--impl reference: the reference's own CPU implementation of the path (natural_es.train verbatim from oracle/_ref),
     all host cores, a bounded sample of the population per step; rank 0 only."""
@@ -602,27 +623,6 @@ def measure_cma(torch, dist, timed, max_over_ranks, world, rank, dev, hbm_peak, 
         r['cpu_baseline'] = cma_cpu_baseline(n, lam)
     out.append(r)
     return out
-
-
-def cma_cpu_baseline(n, lam):
-    """fp64 numpy restatement of the rank-mu update (BLAS, all host threads): pycma is unavailable."""
-    try:
-        from oracle import cma_oracle as co
-        rs = np.random.RandomState(0)
-        Y = rs.randn(lam, n)
-        w = rs.rand(lam)
-        C = np.eye(n)
-        pc = rs.randn(n)
-        co.cov_update(C, co.rank_mu_delta(Y, w), pc, 0.001, 0.009, w.sum())
-        t0 = time.perf_counter()
-        reps = 3 if n <= 1024 else 1
-        for _ in range(reps):
-            co.cov_update(C, co.rank_mu_delta(Y, w), pc, 0.001, 0.009, w.sum())
-        sec = (time.perf_counter() - t0) / reps
-        return {'value': 1.0 / sec, 'unit': 'updates/s', 'cores': os.cpu_count(), 'kind': 'port',
-                'sample': 'fp64 numpy restatement (BLAS Y^T diag(w) Y + covariance update), %d repetition(s); pycma unavailable' % reps}
-    except Exception as e:
-        return {'value': None, 'unit': 'updates/s', 'cores': None, 'kind': 'port', 'sample': 'failed: %s' % str(e)[:200]}
 
 
 def _guard_stdout():
