@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, 'libdes_b200.so')
+# DES_LIB_PATH selects another build of the same library (kernel experiments: scripts/build_variant.sh)
+LIB_PATH = os.environ.get('DES_LIB_PATH') or os.path.join(_PKG, 'libdes_b200.so')
 
 DES_OK = 0
 FWD_FP32, FWD_F16, FWD_F16X3 = 0, 1, 2

@@ -92,6 +92,7 @@ class CMAEvolutionStrategy:
         BD = (self.B * self.D).to(torch.float32)                 # columns scaled by D
         y = z.to(torch.float32) @ BD.T                           # [n_local, n] x [n, n]  (library GEMM)
         self.X = (self.m + self.sigma * y.to(torch.float64)).to(torch.float32).contiguous()
+        self._y_of_X = y          # tell() reuses it: (X - m)/sigma from the fp32-rounded X loses |m|/sigma * 6e-8
         return self.X
 
     def gather_cost(self, cost_local):
@@ -119,7 +120,10 @@ class CMAEvolutionStrategy:
         pos = torch.empty_like(order)
         pos[order] = torch.arange(self.lam, device=self.device)
         w_loc64 = self.w64[pos[self.offset:self.offset + self.n_local]]
-        Y = (X.to(torch.float64) - self.m) / self.sigma                       # y_i of the local members
+        if X is getattr(self, 'X', None) and getattr(self, '_y_of_X', None) is not None:
+            Y = self._y_of_X.to(torch.float64)                                # exactly the y that ask() sampled
+        else:
+            Y = (X.to(torch.float64) - self.m) / self.sigma                   # foreign solutions: y_i from x_i
         yw = w_loc64 @ Y if self.n_local else torch.zeros(n, dtype=torch.float64, device=self.device)
         # ---- the hot part: rank-mu partial of the shard on our kernel (fp32), summed over ranks.  Sharded runs keep the
         # partial as packed upper-triangular tiles: the all-reduce moves half the bytes of the [n, n] matrix and the

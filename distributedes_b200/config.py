@@ -62,6 +62,11 @@ class ClosedLoopPendulumConfig(BasicConfig):
     200-step episodes per member (config.py:8-9), per-member observations, observation normaliser on."""
 
     def __init__(self, hidden_size=64):
+        # limits of des_rollout_eval (csrc/des_envs.cu): checked here, not at the first generation.  The reference's own
+        # default hidden_size=16 (config.py:27) is below the kernel's 32-unit granularity.
+        if hidden_size % 32 != 0 or not (32 <= hidden_size <= 128):
+            raise ValueError('ClosedLoopPendulumConfig: hidden_size must be 32, 64, 96 or 128 on the device path (got %r)'
+                             % (hidden_size,))
         self.task = 'Pendulum-v0'
         self.clip = 2.0
         self.action_clip = lambda a: np.clip(a, -2, 2)

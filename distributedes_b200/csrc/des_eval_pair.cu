@@ -19,10 +19,17 @@
 //   * theta of the layer-2 tile a generator slot needs is staged by TMA: one thread issues one
 //     cp.async.bulk.tensor.2d (64 x 64 fp32 box of W2) per slot into a two-stage buffer, completion on an mbarrier;
 //     the generator threads read their 32 bytes from shared memory.  (Round 1 used two per-thread cp.async per slot.)
-//   * b2', W3', b3' of a member are generated AFTER its weight tiles (they are needed last), b1' before.
+//   * b1' of a member is generated before its weight tiles, b2', W3', b3' after the tiles of the first output chunk of
+//     layer 2 (the epilogue needs them when that chunk leaves the tensor pipe).
+//
+//   * No relay hop between the CTAs of a pair: the follower's generator / epilogue warps arrive DIRECTLY on the leader's
+//     barriers with a plain remote mbarrier.arrive (no .release.cluster: that lowers to MEMBAR.ALL.GPU + ERRBAR, ~1000
+//     cycles each; round 1 funnelled 14 of them per member through three relay lanes of one warp, and ncu showed that warp
+//     58 % stalled on them — the pair's critical path).  The stores a remote arrive publishes are complete before it is
+//     issued: generators execute fence.proxy.async after their st.shared, epilogue warps tcgen05.wait::st / ::ld.
 //
 // Warp roles: warps 0-7 epilogue (two per TMEM lane quadrant, alternating 32-column groups), warps 8-23 weight
-// generators, warp 24 TMEM allocator + MMA issuer (leader CTA) / barrier relay lanes (follower CTA).
+// generators, warp 24 TMEM allocator + MMA issuer (leader CTA only), warp 25 TMA producer of the theta boxes.
 #include <cuda.h>
 #include <stdlib.h>
 #include "des_common.cuh"
@@ -38,12 +45,17 @@ constexpr int kGenWarps = 16;
 constexpr int kGenThreads = kGenWarps * 32;
 constexpr int kEpiWarps = 8;
 constexpr int kMmaWarp = kEpiWarps + kGenWarps;
-constexpr int kThreads = (kEpiWarps + kGenWarps + 1) * 32;
+constexpr int kProdWarp = kMmaWarp + 1;
+constexpr int kThreads = (kEpiWarps + kGenWarps + 2) * 32;
 constexpr int kK1 = 32;                       // layer-1 K (state_dim zero-padded): 2 k-steps of 16
 constexpr int kMaxA = 8;
 constexpr int kNC = 128;                      // accumulator chunk = MMA N of the pair (64 rows of B per CTA)
 constexpr int kThetaStage = 64 * 64 * 4;      // one TMA box of W2: 64 rows x 64 columns fp32
-// Register budget: the kernel is launched with kLaunchRegs per thread (__maxnreg__), i.e. a pool of 800 x 72 = 57 600;
+#ifndef DES_PAIR_THETA_STAGES
+#define DES_PAIR_THETA_STAGES 2
+#endif
+constexpr int kThStages = DES_PAIR_THETA_STAGES;
+// Register budget: the kernel is launched with kLaunchRegs per thread (__maxnreg__), i.e. a pool of 832 x 72 = 59 904;
 // setmaxnreg then moves registers from the generators to the epilogue warps.  The sum must fit the pool, or the
 // epilogue's setmaxnreg.inc never returns.
 #ifndef DES_PAIR_GEN_REGS
@@ -55,9 +67,10 @@ constexpr int kThetaStage = 64 * 64 * 4;      // one TMA box of W2: 64 rows x 64
 #ifndef DES_PAIR_MMA_REGS
 #define DES_PAIR_MMA_REGS 64
 #endif
-constexpr int kLaunchRegs = 72;     // 25 warps are allocated as 28 (granularity 4): 28 x 32 x 72 <= 65 536
+constexpr int kLaunchRegs = 72;     // 26 warps are allocated as 28 (granularity 4): 28 x 32 x 72 <= 65 536
 constexpr int kGenRegs = DES_PAIR_GEN_REGS, kEpiRegs = DES_PAIR_EPI_REGS, kMmaRegs = DES_PAIR_MMA_REGS;
-static_assert(kGenWarps * 32 * kGenRegs + kEpiWarps * 32 * kEpiRegs + 32 * kMmaRegs <= kThreads * kLaunchRegs,
+constexpr int kProdRegs = 24;
+static_assert(kGenWarps * 32 * kGenRegs + kEpiWarps * 32 * kEpiRegs + 32 * kMmaRegs + 32 * kProdRegs <= kThreads * kLaunchRegs,
               "setmaxnreg budget exceeds the registers the CTA is launched with");
 
 template <int H, bool X3>
@@ -85,7 +98,7 @@ struct Args {
 
 struct Bars {
     uint64_t slot_full[16], slot_empty[16];
-    uint64_t th_full[2], th_empty[2];
+    uint64_t th_full[4], th_empty[4];
     uint64_t s1_full[2], s1_empty[2], s2_full[2], s2_empty[2];
     uint64_t d1_full[2], h_ready[2], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
@@ -106,6 +119,12 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
     uint64_t rd;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(pk2(a)), "l"(pk2(b)));
     return upk2(rd);
+}
+// plain arrive on the barrier at the same offset in CTA `rank` of the cluster (no cluster-scope release: see header)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(bar), "r"(rank));
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -170,8 +189,8 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *xs = smem;                                                    // X tile (hi [, lo])
     uint8_t *ring = xs + C::X_TILE_BYTES;                                  // n_slots * SLOT_BYTES
-    uint8_t *th_stage = ring + (size_t)a.n_slots * C::SLOT_BYTES;          // 2 x 16 KB TMA destinations
-    float *small1 = reinterpret_cast<float *>(th_stage + 2 * kThetaStage); // [2][H]: b1' * 2log2e
+    uint8_t *th_stage = ring + (size_t)a.n_slots * C::SLOT_BYTES;          // kThStages x 16 KB TMA destinations
+    float *small1 = reinterpret_cast<float *>(th_stage + kThStages * kThetaStage); // [2][H]: b1' * 2log2e
     const int s2_floats = H + a.a4 * H + kMaxA;                            // b2' * 2log2e | W3' [a4][H] | b3'[8]
     float *small2 = small1 + 2 * H;                                        // [2][s2_floats]
     Bars *bars = reinterpret_cast<Bars *>((reinterpret_cast<uintptr_t>(small2 + 2 * s2_floats) + 15) & ~(uintptr_t)15);
@@ -184,22 +203,24 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
 
     if (warp == kMmaWarp) {
         if (lane == 0) {
-            const uint32_t relay = rank == 0 ? 1u : 0u;      // the leader's copies also collect the follower's relay
+            // barriers the MMA thread waits on live in the leader only and collect the warps of BOTH CTAs
             for (int s = 0; s < a.n_slots; ++s) {
-                mbar_init(smem_u32(&bars->slot_full[s]), kGenWarps + relay);
+                mbar_init(smem_u32(&bars->slot_full[s]), 2 * kGenWarps);
                 mbar_init(smem_u32(&bars->slot_empty[s]), 1);
             }
-            for (int p = 0; p < 2; ++p) {
+            for (int p = 0; p < kThStages; ++p) {
                 mbar_init(smem_u32(&bars->th_full[p]), 1);
                 mbar_init(smem_u32(&bars->th_empty[p]), kGenWarps);
+            }
+            for (int p = 0; p < 2; ++p) {
                 mbar_init(smem_u32(&bars->s1_full[p]), kGenWarps);
                 mbar_init(smem_u32(&bars->s1_empty[p]), kEpiWarps);
                 mbar_init(smem_u32(&bars->s2_full[p]), kGenWarps);
                 mbar_init(smem_u32(&bars->s2_empty[p]), kEpiWarps);
                 mbar_init(smem_u32(&bars->d1_full[p]), 1);
-                mbar_init(smem_u32(&bars->h_ready[p]), kEpiWarps + relay);
+                mbar_init(smem_u32(&bars->h_ready[p]), 2 * kEpiWarps);
                 mbar_init(smem_u32(&bars->acc_full[p]), 1);
-                mbar_init(smem_u32(&bars->acc_empty[p]), kEpiWarps + relay);
+                mbar_init(smem_u32(&bars->acc_empty[p]), 2 * kEpiWarps);
             }
             fence_barrier_init();
         }
@@ -233,6 +254,11 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
 
+    // arrive on the LEADER's copy of a barrier (local for the leader, one remote arrive for the follower)
+    auto arrive_leader = [&](uint64_t *bar) {
+        if (rank == 0) mbar_arrive(smem_u32(bar));
+        else mbar_arrive_remote(smem_u32(bar), 0);
+    };
     const int64_t first = blockIdx.x / 2;
     const int64_t stride = gridDim.x / 2;
     const int64_t n_mine = a.n_local > first ? (a.n_local - first + stride - 1) / stride : 0;
@@ -301,28 +327,23 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                 }
             }
         }
-        if (rank == 1 && lane < 3) {
-            // ---- follower CTA: relay completed local phases to the leader's barriers, in the leader's wait order
-            if (lane == 0) {                      // slot_full: one relay per ring slot
-                uint32_t rs = 0, rph = 0;
-                for (int64_t i = 0; i < n_mine * C::SLOTS_PER_MEMBER; ++i) {
-                    mbar_wait(smem_u32(&bars->slot_full[rs]), rph);
-                    mbar_arrive_cluster(smem_u32(&bars->slot_full[rs]), 0);
-                    if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
-                }
-            } else if (lane == 1) {               // acc_empty: one relay per accumulator-stage use
-                for (int64_t u = 0; u < n_mine * C::NCH; ++u) {
-                    const uint32_t st = (uint32_t)u & 1, ph = (uint32_t)(u >> 1) & 1;
-                    mbar_wait(smem_u32(&bars->acc_empty[st]), ph);
-                    mbar_arrive_cluster(smem_u32(&bars->acc_empty[st]), 0);
-                }
-            } else {                              // h_ready: one relay per (member, chunk)
-                for (int64_t v = 0; v < n_mine; ++v) {
-                    for (int nc = 0; nc < C::NCH; ++nc) {
-                        mbar_wait(smem_u32(&bars->h_ready[nc]), (uint32_t)v & 1);
-                        mbar_arrive_cluster(smem_u32(&bars->h_ready[nc]), 0);
-                    }
-                }
+    } else if (warp == kProdWarp) {
+        // =================================== TMA producer of the theta boxes (one thread) ==============================
+        // theta of a layer-2 tile does not depend on the member: the 64 x 64 fp32 box of fc2.weight a generator slot needs
+        // is refilled into its stage the moment all sixteen generator warps have read the stage's previous box
+        reg_dealloc<kProdRegs>();
+        if (lane == 0) {
+            const uint32_t total = (uint32_t)n_mine * (uint32_t)(C::NCH * C::KAT);
+            const int row_base = 64 * (int)rank;
+            uint32_t w = 0;                                      // layer-2 slot of the member: (nc, ka) = (w / KAT, w % KAT)
+            for (uint32_t q = 0; q < total; ++q) {
+                const uint32_t stg = q % kThStages, use = q / kThStages;
+                if (use > 0) mbar_wait(smem_u32(&bars->th_empty[stg]), (use - 1) & 1);
+                const uint32_t bar = smem_u32(&bars->th_full[stg]);
+                mbar_expect_tx(bar, kThetaStage);
+                tma_load_2d(smem_u32(th_stage + stg * kThetaStage), &w2_map, (int)(w % C::KAT) * 64,
+                            (int)(w / C::KAT) * kNC + row_base, bar);
+                if (++w == (uint32_t)(C::NCH * C::KAT)) w = 0;
             }
         }
     } else if (warp < kEpiWarps) {
@@ -380,7 +401,7 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                 tmem_wait_st();                       // this chunk of H1 is complete: its k-atoms may be consumed
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bars->h_ready[nc]));
+                if (lane == 0) arrive_leader(&bars->h_ready[nc]);
             }
             if (lane == 0) mbar_arrive(smem_u32(&bars->s1_empty[p]));
         };
@@ -405,7 +426,7 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                 if (gi == 1) {                                 // every load of this accumulator stage has landed
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[st]));
+                    if (lane == 0) arrive_leader(&bars->acc_empty[st]);
                 }
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
@@ -501,21 +522,7 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
         uint32_t rs = 0, rph = 0;                                       // ring cursor: slot index and phase
         const int r2 = gtid >> 3, c82 = gtid & 7;
         const int row_base = 64 * (int)rank;                            // this CTA's 64 rows of every 128-row chunk
-        // theta of a layer-2 tile does not depend on the member: TMA stages the 64 x 64 fp32 box one slot ahead
-        uint32_t tq = 0;                                                // layer-2 slots generated so far (stage = tq & 1)
-        const int64_t tq_total = n_mine * (C::NCH * C::KAT);
-        auto theta_issue = [&](uint32_t q) {                            // gtid == 0 only
-            const uint32_t stg = q & 1;
-            const int w = (int)(q % (uint32_t)(C::NCH * C::KAT));
-            const int nc = w / C::KAT, ka = w % C::KAT;
-            const uint32_t bar = smem_u32(&bars->th_full[stg]);
-            mbar_expect_tx(bar, kThetaStage);
-            tma_load_2d(smem_u32(th_stage + stg * kThetaStage), &w2_map, ka * 64, nc * kNC + row_base, bar);
-        };
-        if (gtid == 0) {
-            if (tq_total > 0) theta_issue(0);
-            if (tq_total > 1) theta_issue(1);
-        }
+        uint32_t tq = 0;                                                // layer-2 slots generated so far (theta stage = tq % kThStages)
         const float bsc = X3 ? kTwoLog2e : 1.0f;     // the f16x3 epilogue evaluates tanh(v + b) as 1 - 2/(1 + 2^(v c + b c))
         uint32_t mi = 0;
         for (int64_t i = 0; i < n_mine; ++i, ++mi) {
@@ -571,19 +578,14 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bars->slot_full[s]));
+                if (lane == 0) arrive_leader(&bars->slot_full[s]);
             }
             // ---- layer-2 tiles: rows [128nc + 64 rank, +64) x k [64ka, +64) of W2': one octet per thread
             for (int nc = 0; nc < C::NCH; ++nc) {
                 for (int ka = 0; ka < C::KAT; ++ka) {
                     const uint32_t s = rs, sph = rph;
                     if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
-                    const uint32_t stg = tq & 1, tph = (tq >> 1) & 1;
-                    if (gtid == 0 && tq >= 1 && (int64_t)tq + 1 < tq_total) {
-                        // the stage slot tq-1 used has been read by all sixteen warps: refill it with the box of slot tq+1
-                        mbar_wait(smem_u32(&bars->th_empty[stg ^ 1]), ((tq - 1) >> 1) & 1);
-                        theta_issue(tq + 1);
-                    }
+                    const uint32_t stg = tq % kThStages, tph = (tq / kThStages) & 1;
                     ++tq;
                     const int j0 = L.off_w2 + (nc * kNC + row_base + r2) * H + ka * 64 + c82 * 8;
                     const uint4 x0 = philox4x32((uint32_t)(j0 >> 2), member, gen, kStreamNesEps, a.key);
@@ -605,30 +607,32 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                     store_octet<X3>(ring + (size_t)s * C::SLOT_BYTES, r2, c82, w);
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&bars->slot_full[s]));
+                    if (lane == 0) arrive_leader(&bars->slot_full[s]);
+                }
+                if (nc == 0) {
+                    // ---- b2', W3', b3': needed by the epilogue of layer 2, i.e. once the first output chunk has left the tensor pipe
+                    mbar_wait(smem_u32(&bars->s2_empty[p]), ((mi >> 1) & 1) ^ 1);
+                    float *sm2 = small2 + p * s2_floats;
+                    for (int k = gtid; k < H / 4; k += kGenThreads) {
+                        const float4 v2 = perturbed_quad((uint32_t)((L.off_b2 >> 2) + k), member, gen, kStreamNesEps, a.key,
+                                                         a.neg2ln2_sigma2, __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_b2) + k));
+                        reinterpret_cast<float4 *>(sm2)[k] = make_float4(v2.x * bsc, v2.y * bsc, v2.z * bsc, v2.w * bsc);
+                    }
+                    for (int k = gtid; k < L.A * H / 4; k += kGenThreads)            // W3' [q][n] row-major: aligned quads
+                        reinterpret_cast<float4 *>(sm2 + H)[k] =
+                            perturbed_quad((uint32_t)((L.off_w3 >> 2) + k), member, gen, kStreamNesEps, a.key, a.neg2ln2_sigma2,
+                                           __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_w3) + k));
+                    if (gtid < L.A) {
+                        const int j = L.off_b3 + gtid;
+                        const float4 z = noise_quad((uint32_t)(j >> 2), member, gen, kStreamNesEps, a.key);
+                        const int el = j & 3;
+                        const float zz = el == 0 ? z.x : (el == 1 ? z.y : (el == 2 ? z.z : z.w));
+                        sm2[H + a.a4 * H + gtid] = __fmaf_rn(a.sigma, zz, __ldg(a.theta + j));
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bars->s2_full[p]));
                 }
             }
-            // ---- b2', W3', b3' (needed last: the epilogue of layer 2)
-            mbar_wait(smem_u32(&bars->s2_empty[p]), ((mi >> 1) & 1) ^ 1);
-            float *sm2 = small2 + p * s2_floats;
-            for (int k = gtid; k < H / 4; k += kGenThreads) {
-                const float4 v2 = perturbed_quad((uint32_t)((L.off_b2 >> 2) + k), member, gen, kStreamNesEps, a.key,
-                                                 a.neg2ln2_sigma2, __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_b2) + k));
-                reinterpret_cast<float4 *>(sm2)[k] = make_float4(v2.x * bsc, v2.y * bsc, v2.z * bsc, v2.w * bsc);
-            }
-            for (int k = gtid; k < L.A * H / 4; k += kGenThreads)            // W3' [q][n] row-major: aligned quads
-                reinterpret_cast<float4 *>(sm2 + H)[k] =
-                    perturbed_quad((uint32_t)((L.off_w3 >> 2) + k), member, gen, kStreamNesEps, a.key, a.neg2ln2_sigma2,
-                                   __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_w3) + k));
-            if (gtid < L.A) {
-                const int j = L.off_b3 + gtid;
-                const float4 z = noise_quad((uint32_t)(j >> 2), member, gen, kStreamNesEps, a.key);
-                const int el = j & 3;
-                const float zz = el == 0 ? z.x : (el == 1 ? z.y : (el == 2 ? z.z : z.w));
-                sm2[H + a.a4 * H + gtid] = __fmaf_rn(a.sigma, zz, __ldg(a.theta + j));
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars->s2_full[p]));
         }
     }
     tc_fence_before();
@@ -678,7 +682,7 @@ static int launch(Args &a, cudaStream_t st) {
     }
     a.a4 = a.L.A > 4 ? 8 : 4;
     const size_t s2_floats = (size_t)H + (size_t)a.a4 * H + kMaxA;
-    const size_t fixed = 1024 + C::X_TILE_BYTES + 2 * kThetaStage + (2 * H + 2 * s2_floats) * sizeof(float) + 16 + sizeof(Bars) +
+    const size_t fixed = 1024 + C::X_TILE_BYTES + kThStages * kThetaStage + (2 * H + 2 * s2_floats) * sizeof(float) + 16 + sizeof(Bars) +
                          2 * 128 * (size_t)a.a4 * sizeof(float);
     int n_slots = (int)((227 * 1024 - fixed) / C::SLOT_BYTES);
     if (n_slots > 16) n_slots = 16;

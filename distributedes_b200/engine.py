@@ -104,6 +104,9 @@ class NESEngine:
             # what the kernels read: the raw tape, or its normalised image refreshed every generation
             self.obs = torch.empty_like(self.obs_raw) if self.normalize_obs else self.obs_raw
             self._graph = None
+            if getattr(self, 'T', None) is not None and int(obs.shape[0]) != self.T and hasattr(self.k, 'eval_workspace'):
+                # a new tape length may be a multi-pass tensor-core shape: size its tile cache for the new T
+                self.eval_ws = self.k.eval_workspace(self.d0, self.H, self.A, int(obs.shape[0]), self.precision, self.device)
         self.T = int(obs.shape[0])
 
     # -- the three phases around the two collectives -------------------------------------------------------
@@ -226,6 +229,12 @@ class RolloutEngine(NESEngine):
                  horizon=None, action_noise_std=0.0, normalize_obs=True, **kw):
         if task not in self.ENVS:
             raise ValueError('closed-loop environments available on the device: %s (got %r)' % (sorted(self.ENVS), task))
+        if int(hidden) % 32 != 0 or not (32 <= int(hidden) <= 128):
+            raise ValueError('RolloutEngine: hidden must be 32, 64, 96 or 128 (des_rollout_eval keeps 4 units per lane); got %r'
+                             % (hidden,))
+        if not (1 <= int(repetitions) <= 10):
+            raise ValueError('RolloutEngine: repetitions must be in [1, 10] (one warp steps them in lockstep); got %r'
+                             % (repetitions,))
         e = self.ENVS[task]
         self.env_id, self.horizon = e['env'], int(horizon or e['horizon'])
         self.action_noise_std = float(action_noise_std)

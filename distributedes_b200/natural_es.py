@@ -112,25 +112,42 @@ def test(config, solution, stats, engine=None):
     return np.mean(rewards), np.std(rewards) / config.test_repetitions
 
 
-def _launch_entry(rank, world_size, config_fn, port, result):
+def _launch_entry(rank, world_size, config_fn, port, result_path):
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world_size)
     try:
         out = train(config_fn())
         if rank == 0:
-            result.put(out)
+            # a file, not a pipe: a SimpleQueue.put() of a long run's result blocks once the 64 KiB pipe buffer is full
+            # while the parent is still joining the children
+            with open(result_path, 'wb') as f:
+                pickle.dump(out, f)
     finally:
         dist.destroy_process_group()
 
 
-def launch(config_fn, world_size, port=29533):
+def _free_port():
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def launch(config_fn, world_size, port=None):
     """Spawn one process per GPU and run train(config_fn()) in each (the reference's `for w in workers:
-    w.start()`, natural_es.py:44-45).  config_fn must be picklable (module-level function)."""
+    w.start()`, natural_es.py:44-45).  config_fn must be picklable (module-level function); `port` defaults to a
+    free one on 127.0.0.1."""
+    import tempfile
     import torch.multiprocessing as mp
-    ctx = mp.get_context('spawn')
-    result = ctx.SimpleQueue()
-    mp.spawn(_launch_entry, args=(world_size, config_fn, port, result), nprocs=world_size, join=True)
-    return result.get()
+    port = int(port) if port else _free_port()
+    fd, path = tempfile.mkstemp(suffix='.des_result')
+    os.close(fd)
+    try:
+        mp.spawn(_launch_entry, args=(world_size, config_fn, port, path), nprocs=world_size, join=True)
+        with open(path, 'rb') as f:
+            return pickle.load(f)
+    finally:
+        os.unlink(path)
 
 
 # ---- run bookkeeping (natural_es.py:113-124; SURVEY 8f row 4) ----------------------------------------------------------
@@ -157,33 +174,48 @@ def multi_runs(config, runs=10, log_dir='log', data_dir='data'):
     return stats
 
 
+_CKPT_SCALARS = ('sigma', 'lr', 'wd', 'beta1', 'beta2', 'epsilon', 'clip')
+
+
 def save_checkpoint(engine, path):
     """Everything a run needs to resume: theta, Adam (m, v, beta^t, t), generation counter, observation statistics,
-    seed.  (The reference keeps no training checkpoint)"""
+    seed, and the hyper-parameters the run was started with (checked on load).  Plain arrays in an .npz container:
+    loading never unpickles.  (The reference keeps no training checkpoint)"""
     from . import ops
     st = ops.read_state(engine.state)
     blob = dict(theta=engine.theta_numpy(), adam_m=engine.adam_m.cpu().numpy(), adam_v=engine.adam_v.cpu().numpy(),
-                state=st, seed=engine.seed, pop_size=engine.N, dims=(engine.d0, engine.H, engine.A),
-                obs_stats=engine.obs_stats.cpu().numpy() if engine.normalize_obs else None)
+                generation=np.uint64(st['generation']), adam_t=np.uint64(st['adam_t']),
+                beta1_t=np.float64(st['beta1_t']), beta2_t=np.float64(st['beta2_t']),
+                seed=np.uint64(engine.seed), pop_size=np.int64(engine.N), dims=np.asarray([engine.d0, engine.H, engine.A]),
+                precision=np.str_(engine.precision), normalize_obs=np.bool_(engine.normalize_obs),
+                hyper=np.asarray([getattr(engine, k) for k in _CKPT_SCALARS], dtype=np.float64))
+    if engine.normalize_obs:
+        blob['obs_stats'] = engine.obs_stats.cpu().numpy()
     with open(path, 'wb') as f:
-        pickle.dump(blob, f)
+        np.savez(f, **blob)
 
 
 def load_checkpoint(engine, path):
-    """Restore a checkpoint written by save_checkpoint into a compatible engine (same MLP dims and population)."""
-    import ctypes as C
+    """Restore a checkpoint written by save_checkpoint into an engine built with the same MLP dims, population,
+    precision, normaliser setting and optimiser hyper-parameters (anything else raises: resuming into a different
+    configuration would silently continue with inconsistent state)."""
     from ._lib import State
-    with open(path, 'rb') as f:
-        blob = pickle.load(f)
-    if tuple(blob['dims']) != (engine.d0, engine.H, engine.A) or blob['pop_size'] != engine.N:
-        raise ValueError('checkpoint is for dims %r / population %r' % (blob['dims'], blob['pop_size']))
-    engine.theta.copy_(torch.from_numpy(blob['theta']))
-    engine.adam_m.copy_(torch.from_numpy(blob['adam_m']))
-    engine.adam_v.copy_(torch.from_numpy(blob['adam_v']))
-    s = blob['state']
-    raw = bytes(State(s['generation'], s['adam_t'], s['beta1_t'], s['beta2_t']))
-    engine.state.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
-    engine.seed = blob['seed']
-    engine.generation_index = int(s['generation'])
-    if engine.normalize_obs and blob['obs_stats'] is not None:
-        engine.obs_stats.copy_(torch.from_numpy(blob['obs_stats']))
+    with np.load(path, allow_pickle=False) as blob:
+        if tuple(int(v) for v in blob['dims']) != (engine.d0, engine.H, engine.A) or int(blob['pop_size']) != engine.N:
+            raise ValueError('checkpoint is for dims %r / population %r' % (blob['dims'].tolist(), int(blob['pop_size'])))
+        if str(blob['precision']) != engine.precision or bool(blob['normalize_obs']) != engine.normalize_obs:
+            raise ValueError('checkpoint was written with precision=%s normalize_obs=%s; the engine has %s / %s' %
+                             (blob['precision'], bool(blob['normalize_obs']), engine.precision, engine.normalize_obs))
+        mine = np.asarray([getattr(engine, k) for k in _CKPT_SCALARS], dtype=np.float64)
+        if not np.array_equal(mine, blob['hyper']):
+            raise ValueError('checkpoint hyper-parameters %r differ from the engine\'s %r (%s)' %
+                             (blob['hyper'].tolist(), mine.tolist(), ', '.join(_CKPT_SCALARS)))
+        engine.theta.copy_(torch.from_numpy(blob['theta']))
+        engine.adam_m.copy_(torch.from_numpy(blob['adam_m']))
+        engine.adam_v.copy_(torch.from_numpy(blob['adam_v']))
+        raw = bytes(State(int(blob['generation']), int(blob['adam_t']), float(blob['beta1_t']), float(blob['beta2_t'])))
+        engine.state.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+        engine.seed = int(blob['seed'])
+        engine.generation_index = int(blob['generation'])
+        if engine.normalize_obs:
+            engine.obs_stats.copy_(torch.from_numpy(blob['obs_stats']))

@@ -65,12 +65,24 @@ class Adam:
 
 
 class SharedStats:
-    """utils.py:59-106 surface; only the empty (n == 0 -> identity) state is supported in this round."""
+    """utils.py:59-106: running mean / variance / count of the observations, fp32 like the reference's torch tensors.
+    This is the master-side bookkeeping object (2*d0+1 numbers); the per-generation statistics of whole tapes or
+    rollouts are produced on the device (des_obs_stats_merge / des_obs_stats_merge_totals) and land here through
+    load_state_dict / merge."""
 
     def __init__(self, o_size):
         self.m = np.zeros(o_size, dtype=np.float32)
         self.v = np.zeros(o_size, dtype=np.float32)
         self.n = np.zeros(1, dtype=np.float32)
+
+    def feed(self, o):
+        """utils.py:68-73, one observation (fp32 arithmetic in the reference's order)."""
+        o = np.asarray(o, dtype=np.float32).reshape(self.m.shape)
+        n = self.n[0]
+        new_m = self.m * (n / (n + np.float32(1))) + o / (n + np.float32(1))
+        self.v[:] = self.v * (n / (n + np.float32(1))) + (o - self.m) * (o - new_m) / (n + np.float32(1))
+        self.m[:] = new_m
+        self.n += np.float32(1)
 
     def zero(self):
         self.m[:] = 0
@@ -81,28 +93,64 @@ class SharedStats:
         self.m[:], self.v[:], self.n[:] = stats.m, stats.v, stats.n
 
     def merge(self, B):
-        if B.n[0] != 0:
-            raise NotImplementedError('host-side merging is not supported: use NESEngine(normalize_obs=True), which keeps '
-                                      'SharedStats on the device (des_obs_stats_merge)')
+        """utils.py:85-96 (Chan merge), fp32 in the reference's order; merging empty statistics is a no-op (the reference
+        divides 0/0 there and poisons the statistics — not replicated)."""
+        n_A, n_B = self.n[0], B.n[0]
+        if n_B == 0:
+            return
+        n = n_A + n_B
+        delta = B.m - self.m
+        m = self.m + delta * n_B / n
+        v = self.v * n_A + B.v * n_B + delta * delta * n_A * n_B / n
+        v = v / n
+        self.m[:] = m
+        self.v[:] = v
+        self.n += B.n
 
     def state_dict(self):
         return {'m': self.m, 'v': self.v, 'n': self.n}
 
     def load_state_dict(self, saved):
-        self.m, self.v, self.n = (np.asarray(saved[k], dtype=np.float32) for k in ('m', 'v', 'n'))
+        self.m, self.v, self.n = (np.array(saved[k], dtype=np.float32) for k in ('m', 'v', 'n'))
+
+    def as_device_tensor(self, device):
+        """[m | v | n] fp32 on the device: the layout des_obs_normalize / des_obs_stats_merge take."""
+        return torch.from_numpy(np.concatenate([self.m, self.v, self.n]).astype(np.float32)).to(device)
 
 
 class StaticNormalizer:
-    """utils.py:37-57; with empty offline stats it is the identity (utils.py:48-49)."""
+    """utils.py:37-57: feeds the online statistics and applies the offline ones, (o - m)/sqrt(v + 1e-6), or passes the
+    observation through while the offline statistics are empty (utils.py:48-49).  Single observations are handled here
+    (host bookkeeping, as in the reference's master process); whole tapes go through normalize_tape (device)."""
 
     def __init__(self, o_size):
         self.offline_stats = SharedStats(o_size)
         self.online_stats = SharedStats(o_size)
 
     def __call__(self, o_):
-        if self.offline_stats.n[0] != 0:
-            raise NotImplementedError('non-empty statistics live on the device: NESEngine(normalize_obs=True)')
-        return o_
+        scalar = np.isscalar(o_)
+        o = np.asarray([o_] if scalar else o_, dtype=np.float32)
+        self.online_stats.feed(o.reshape(-1))
+        if self.offline_stats.n[0] == 0:
+            return o_
+        std = (self.offline_stats.v + np.float32(1e-6)) ** np.float32(.5)
+        out = ((o.reshape(-1) - self.offline_stats.m) / std).astype(np.float32)
+        return float(out[0]) if scalar else out.reshape(np.shape(o_))
+
+    def normalize_tape(self, obs_dev, device):
+        """The whole observation tape on the device: des_obs_normalize with the offline statistics, and the tape's
+        statistics Chan-merged into the online ones by des_obs_stats_merge (what feeding every row would accumulate,
+        up to fp32 rounding order)."""
+        from . import ops
+        T = int(obs_dev.shape[0])
+        online = self.online_stats.as_device_tensor(device)
+        ops.obs_stats_merge(online, obs_dev, T)
+        st = online.cpu().numpy()
+        d0 = self.online_stats.m.size
+        self.online_stats.load_state_dict({'m': st[:d0], 'v': st[d0:2 * d0], 'n': st[2 * d0:]})
+        if self.offline_stats.n[0] == 0:
+            return obs_dev
+        return ops.obs_normalize(obs_dev, self.offline_stats.as_device_tensor(device))
 
 
 class Evaluator:
@@ -130,8 +178,8 @@ class Evaluator:
 
     def single_run(self):
         from . import ops
-        self.state_normalizer(self.env.obs[0])       # identity check (raises if stats are non-empty)
+        obs = self.state_normalizer.normalize_tape(self._obs, self.device)       # utils.py:131, whole tape at once
         theta = torch.from_numpy(self.model.get_weight()).to(self.device)
-        fit = ops.nes_eval(theta, self._obs, self._target, hidden=self.config.hidden_size, sigma=0.0,
+        fit = ops.nes_eval(theta, obs, self._target, hidden=self.config.hidden_size, sigma=0.0,
                            clip=self.config.clip, seed=0, generation=0, member_offset=0, n_local=1, precision='fp32')
         return float(fit[0]), self.env.tape_len

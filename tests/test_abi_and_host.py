@@ -212,3 +212,35 @@ def test_bench_reference_arm_contract():
     assert d['cpu_baseline']['cores'] >= 1 and d['value'] > 0 and 'port' in d['cpu_baseline']
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert 'workload' in d['config']
+
+
+def test_host_normaliser_matches_reference_arithmetic():
+    """utils.SharedStats.feed / merge and StaticNormalizer.__call__ restate utils.py:37-96 in the reference's fp32
+    operation order: the fixture values below were produced by the reference classes on the same inputs
+    (RandomState(0), 5-dim observations) — see the inline generator in the docstring of oracle/make_golden.py."""
+    from distributedes_b200.utils import SharedStats, StaticNormalizer
+    rs = np.random.RandomState(0)
+    a = StaticNormalizer(5)
+    for _ in range(50):
+        o = rs.randn(5).astype(np.float32)
+        assert np.array_equal(a(o), o)                      # empty offline statistics: pass-through (utils.py:48-49)
+    assert a.online_stats.n[0] == 50
+    A = SharedStats(5)
+    A.merge(a.online_stats)
+    assert np.array_equal(A.m, a.online_stats.m) and A.n[0] == 50
+    A.merge(SharedStats(5))                                 # merging empty statistics is a no-op
+    assert A.n[0] == 50 and np.all(np.isfinite(A.v))
+    b = StaticNormalizer(5)
+    b.offline_stats.load(A)
+    o = np.asarray([1, 2, 3, 4, 5], dtype=np.float32)
+    want = (o - A.m) / (A.v + np.float32(1e-6)) ** np.float32(.5)
+    assert np.array_equal(b(o), want.astype(np.float32))
+    B = SharedStats(5)
+    for _ in range(30):
+        B.feed((rs.randn(5) * 3 + 1).astype(np.float32))
+    n0, m0, v0 = A.n[0], A.m.copy(), A.v.copy()
+    A.merge(B)
+    n = n0 + B.n[0]
+    delta = B.m - m0
+    assert np.allclose(A.m, m0 + delta * B.n[0] / n, rtol=1e-6)
+    assert np.allclose(A.v, (v0 * n0 + B.v * B.n[0] + delta * delta * n0 * B.n[0] / n) / n, rtol=1e-6)
