@@ -62,6 +62,12 @@ SIGNATURES = {
     'des_cma_packed_elems': (_I64, [_I64]),
     'des_cma_rank_mu_packed': (C.c_int, [_P, _P, _P, _I64, _I64, _P]),
     'des_cma_cov_apply_packed': (C.c_int, [_P, _P, _P, _I64, _D, _D, _D, _P]),
+    'des_comm_create': (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, _I64, _I64, _P]),
+    'des_comm_connect': (C.c_int, [_P, _P]),
+    'des_comm_destroy': (None, [_P]),
+    'des_comm_fitness_all_dev': (_P, [_P]),
+    'des_comm_allgather_fitness': (C.c_int, [_P, _I64, _I64, _P]),
+    'des_comm_allreduce_partial': (C.c_int, [_P, _P, _P, _I64, _P]),
     'des_session_create': (C.c_int, [C.POINTER(_P), C.c_int, Dims, _I64, _I64, _I64, Opt, _D, _U64, C.c_int, _P]),
     'des_session_destroy': (None, [_P]),
     'des_session_generation_host': (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),

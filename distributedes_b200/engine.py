@@ -62,7 +62,26 @@ class NESEngine:
         self.theta = torch.from_numpy(theta0.copy()).to(dev)
         self.adam_m = torch.zeros(self.P, dtype=torch.float64, device=dev)
         self.adam_v = torch.zeros(self.P, dtype=torch.float64, device=dev)
-        self.fitness_all = torch.zeros(self.N, dtype=torch.float32, device=dev)
+        # sharded runs on the real library exchange fitness / partial sums through peer memory (comm.PeerComm: kernels of
+        # this library storing over NVLink); DES_COMM=nccl (or a failure to map the peers) keeps the two NCCL all-reduces
+        self.comm = None
+        import os
+        if self.world > 1 and kernels.__name__.endswith('.ops') and dev.type == 'cuda' and os.environ.get('DES_COMM', 'peer') != 'nccl':
+            try:
+                from .comm import PeerComm
+                self.comm = PeerComm(self.N, self.P, dev, process_group)
+            except RuntimeError as e:
+                import warnings
+                warnings.warn('distributedes_b200: peer-memory exchange unavailable (%s); using NCCL all-reduces' % e)
+                self.comm = None
+            # every rank must take the same path
+            ok = torch.tensor([1 if self.comm is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
+            if int(ok.item()) == 0 and self.comm is not None:
+                self.comm.close()
+                self.comm = None
+        self.fitness_all = self.comm.fitness_all if self.comm is not None else torch.zeros(self.N, dtype=torch.float32, device=dev)
+        self.partial_local = torch.zeros(self.P, dtype=torch.float32, device=dev) if self.comm is not None else None
         self.shaped = torch.zeros(max(self.n_local, 1), dtype=torch.float32, device=dev)[:self.n_local]
         self.partial = torch.zeros(self.P, dtype=torch.float32, device=dev)
         self.update = torch.zeros(self.P, dtype=torch.float32, device=dev)
@@ -76,11 +95,11 @@ class NESEngine:
         self._setup_inputs(obs, target)
         self.generation_index = 0
         self._graph = None
-        # single GPU: the whole generation is one CUDA graph.  With a process group the generation stays eager
-        # unless DES_GRAPH_NCCL=1 (capturing ProcessGroupNCCL collectives is opt-in: it hung on the 2-GPU box).
-        import os
+        # the whole generation is one CUDA graph: always on a single GPU; sharded, when the exchange runs on the
+        # peer-memory kernels (nothing but kernels of this library in the stream).  With NCCL collectives the generation
+        # stays eager unless DES_GRAPH_NCCL=1 (capturing ProcessGroupNCCL collectives hung on the 2-GPU box in round 1).
         self._use_graph = (bool(use_graph) and self.device.type == 'cuda'
-                           and (self.world == 1 or os.environ.get('DES_GRAPH_NCCL') == '1'))
+                           and (self.world == 1 or self.comm is not None or os.environ.get('DES_GRAPH_NCCL') == '1'))
 
     # -- inputs ------------------------------------------------------------------------------------------
     def _setup_inputs(self, obs, target):
@@ -113,23 +132,32 @@ class NESEngine:
     def evaluate(self):
         if self.normalize_obs:        # utils.py:48-51 with the statistics of the previous generations
             self.k.obs_normalize(self.obs_raw, self.obs_stats, out=self.obs)
-        if self.world > 1:
+        if self.world > 1 and self.comm is None:
             self.fitness_all.zero_()
         if self.n_local:
             self.k.nes_eval(self.theta, self.obs, self.target, hidden=self.H, sigma=self.sigma, clip=self.clip,
                             seed=self.seed, state=self.state, member_offset=self.offset, n_local=self.n_local,
                             precision=self.precision, out=self.fitness_all[self.offset:self.offset + self.n_local],
                             workspace=self.eval_ws)
-        if self.world > 1:
-            dist.all_reduce(self.fitness_all, group=self.pg)
+        self._gather_fitness()
         return self.fitness_all
+
+    def _gather_fitness(self):
+        if self.world > 1:
+            if self.comm is not None:
+                self.comm.allgather_fitness(self.offset, self.n_local)     # shard -> every peer's fitness_all, flag barrier
+            else:
+                dist.all_reduce(self.fitness_all, group=self.pg)
 
     def rank_and_reduce(self):
         self.k.centered_rank(self.fitness_all, self.offset, self.n_local, workspace=self.rank_ws, out=self.shaped)
         self.k.nes_grad_partial(self.shaped, self.P, seed=self.seed, state=self.state, member_offset=self.offset,
-                                workspace=self.grad_ws, out=self.partial)
+                                workspace=self.grad_ws, out=self.partial_local if self.comm is not None else self.partial)
         if self.world > 1:
-            dist.all_reduce(self.partial, group=self.pg)
+            if self.comm is not None:
+                self.comm.allreduce_partial(self.partial_local, self.partial)   # slots over NVLink, summed in rank order
+            else:
+                dist.all_reduce(self.partial, group=self.pg)
         return self.partial
 
     def apply(self):
@@ -243,6 +271,8 @@ class RolloutEngine(NESEngine):
         super().__init__(state_dim=e['state_dim'], hidden=hidden, action_dim=e['action_dim'], pop_size=pop_size,
                          theta0=theta0, obs=None, target=None, sigma=sigma, learning_rate=learning_rate,
                          precision='fp32', normalize_obs=normalize_obs, repetitions=repetitions, **kw)
+        if self.world > 1 and self.normalize_obs:
+            self._use_graph = False          # the observation totals still travel through an NCCL all-reduce
 
     def _setup_inputs(self, obs, target):
         self.T = self.horizon
@@ -255,7 +285,7 @@ class RolloutEngine(NESEngine):
         raise TypeError('RolloutEngine steps the environment on the device; there is no tape to set')
 
     def evaluate(self):
-        if self.world > 1:
+        if self.world > 1 and self.comm is None:
             self.fitness_all.zero_()
         self.obs_totals.zero_()
         if self.n_local:
@@ -266,10 +296,9 @@ class RolloutEngine(NESEngine):
                                 obs_stats=self.obs_stats if self.normalize_obs else None,
                                 totals_out=self.obs_totals if self.normalize_obs else None, workspace=self.roll_ws,
                                 out=self.fitness_all[self.offset:self.offset + self.n_local])
-        if self.world > 1:
-            dist.all_reduce(self.fitness_all, group=self.pg)
-            if self.normalize_obs:
-                dist.all_reduce(self.obs_totals, group=self.pg)
+        self._gather_fitness()
+        if self.world > 1 and self.normalize_obs:
+            dist.all_reduce(self.obs_totals, group=self.pg)
         return self.fitness_all
 
     def _merge_obs_stats(self):

@@ -237,6 +237,30 @@ DES_API int des_cma_rank_mu_packed(float *tiles_out_dev, const float *Y_dev, con
 DES_API int des_cma_cov_apply_packed(float *C_dev, const float *tiles_dev, const float *pc_dev, int64_t n, double decay,
                                      double c1, double cmu, void *stream);
 
+/* ---- exchange steps of a sharded generation over peer memory (NVLink) ------------------------- */
+
+/* One process per GPU on one node.  Replaces the reference's result pipe (natural_es.py:62-75: every worker ships
+ * (epsilon, fitness, steps) to the master) for the two things a shard must exchange: its fitness values (ranks are
+ * global, utils.py:142-148) and its partial sum_i s_i eps_i (natural_es.py:91).  Each rank owns one device block
+ * [fitness_all[N] | slots[world][P]] exported with cudaIpc; the kernels store straight into the peers' blocks and
+ * synchronise with epoch flags kept in device memory (CUDA-graph capturable, no host involvement).
+ *   des_comm_create     allocates the local block on the current device; ipc_handle_out receives 64 bytes to hand to
+ *                       every peer (any transport: torch.distributed all_gather, a file, MPI ...)
+ *   des_comm_connect    all_handles = world x 64 bytes in rank order; maps the peers' blocks (enables P2P access)
+ *   des_comm_fitness_all_dev   the local fitness_all[N]: des_nes_eval writes the shard here
+ *   des_comm_allgather_fitness stores the local shard [member_offset, +n_local) into every peer's fitness_all and
+ *                       returns (on the stream) when every peer's shard has landed here: all ranks then hold the same N values
+ *   des_comm_allreduce_partial  partial_sum_out[j] = sum over ranks r = 0..world-1, in that order, of rank r's
+ *                       partial_dev[j]: bit-identical on every rank (fixed order), so theta needs no broadcast. */
+typedef struct des_comm des_comm;
+DES_API int des_comm_create(des_comm **out, int rank, int world, int64_t N, int64_t P, void *ipc_handle_out);
+DES_API int des_comm_connect(des_comm *c, const void *all_handles);
+DES_API void des_comm_destroy(des_comm *c);
+DES_API float *des_comm_fitness_all_dev(des_comm *c);
+DES_API int des_comm_allgather_fitness(des_comm *c, int64_t member_offset, int64_t n_local, void *stream);
+DES_API int des_comm_allreduce_partial(des_comm *c, float *partial_sum_out_dev, const float *partial_dev, int64_t P,
+                                       void *stream);
+
 /* ---- host-buffer session: the call a reference-side binding makes --------------------------- */
 
 typedef struct des_session des_session;   /* opaque; owns device buffers + a stream */

@@ -14,8 +14,9 @@ pytestmark = pytest.mark.gpu
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, N, precision, use_graph, outdir, gens):
+def _worker(rank, world, port, N, precision, use_graph, outdir, gens, comm):
     sys.path.insert(0, REPO)
+    os.environ['DES_COMM'] = comm           # 'peer': kernels of this library over NVLink peer memory; 'nccl': two all-reduces
     from distributedes_b200.engine import NESEngine
     from oracle import nes_oracle as orc
     torch.cuda.set_device(rank)
@@ -35,13 +36,15 @@ def _worker(rank, world, port, N, precision, use_graph, outdir, gens):
                 theta1 = eng.theta.cpu().numpy()
         torch.cuda.synchronize()
         # results go through files: a SimpleQueue pipe (64 KB) would block the child while the parent joins
+        assert (eng.comm is not None) == (comm == 'peer'), 'exchange path %r was requested' % comm
         np.savez(os.path.join(outdir, 'rank%d.npz' % rank), theta=eng.theta.cpu().numpy(), fitness=fit0, theta1=theta1)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('N,precision,use_graph', [(1000, 'f16x3', False), (1001, 'fp32', False), (4096, 'f16', True)])
-def test_two_gpu_generation_matches_one_gpu(N, precision, use_graph):
+@pytest.mark.parametrize('N,precision,use_graph,comm', [(1000, 'f16x3', False, 'peer'), (1001, 'fp32', False, 'nccl'),
+                                                        (4096, 'f16', True, 'peer'), (1001, 'fp32', True, 'peer')])
+def test_two_gpu_generation_matches_one_gpu(N, precision, use_graph, comm):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     sys.path.insert(0, REPO)
@@ -49,7 +52,7 @@ def test_two_gpu_generation_matches_one_gpu(N, precision, use_graph):
     from oracle import nes_oracle as orc
     import tempfile
     with tempfile.TemporaryDirectory() as outdir:
-        mp.spawn(_worker, args=(2, 29700 + N % 50, N, precision, use_graph, outdir, 3), nprocs=2, join=True)
+        mp.spawn(_worker, args=(2, 29700 + N % 50 + (7 if use_graph else 0), N, precision, use_graph, outdir, 3, comm), nprocs=2, join=True)
         res = []
         for r in range(2):
             z = np.load(os.path.join(outdir, 'rank%d.npz' % r))
