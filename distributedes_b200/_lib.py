@@ -62,6 +62,8 @@ SIGNATURES = {
     'des_cma_packed_elems': (_I64, [_I64]),
     'des_cma_rank_mu_packed': (C.c_int, [_P, _P, _P, _I64, _I64, _P]),
     'des_cma_cov_apply_packed': (C.c_int, [_P, _P, _P, _I64, _D, _D, _D, _P]),
+    'des_cma_tc_workspace_bytes': (_SZ, [_I64, _I64]),
+    'des_cma_rank_mu_tc': (C.c_int, [_P, _P, _P, _I64, _I64, C.c_int, _P, _SZ, _P]),
     'des_comm_create': (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, _I64, _I64, _P]),
     'des_comm_connect': (C.c_int, [_P, _P]),
     'des_comm_destroy': (None, [_P]),

@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG, 'csrc')
 OBJ = os.path.join(PKG, 'build')
 LIB = os.path.join(PKG, 'libdes_b200.so')
 SOURCES = ['des_capi.cu', 'des_noise.cu', 'des_eval_ffma.cu', 'des_eval_tc.cu', 'des_eval_pair.cu', 'des_rank.cu', 'des_update.cu',
-           'des_cma.cu', 'des_envs.cu', 'des_comm.cu']
+           'des_cma.cu', 'des_cma_tc.cu', 'des_envs.cu', 'des_comm.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
 

@@ -262,17 +262,49 @@ def nes_apply(theta, adam_m, adam_v, partial_sum, N, state, *, sigma, learning_r
             _stream()), 'des_nes_apply')
 
 
-def cma_rank_mu(Y, w, out=None):
-    """dC[n,n] = sum_i w_i y_i y_i^T for Y[lambda_local, n] (rank-mu term of es.tell, cma_es.py:90)."""
+_CMA_WS = {}      # (device, n, lambda) -> workspace tensor of the tensor-core rank-mu path
+CMA_TC_MIN_N = 256
+
+
+def _cma_tc_workspace(n, lam, device):
+    key = (str(device), int(n), int(lam))
+    ws = _CMA_WS.get(key)
+    if ws is None:
+        ws = torch.empty(int(_lib.load().des_cma_tc_workspace_bytes(int(n), int(lam))), dtype=torch.uint8, device=device)
+        if len(_CMA_WS) > 8:
+            _CMA_WS.clear()
+        _CMA_WS[key] = ws
+    return ws
+
+
+def _cma_rank_mu(Y, w, out, packed, path):
+    lam, n = Y.shape
+    lib = _lib.load()
+    use_tc = (path == 'tc') or (path is None and n >= CMA_TC_MIN_N and lam >= 1)
+    with _on(Y, 'Y'):
+        if use_tc:
+            ws = _cma_tc_workspace(n, lam, Y.device)
+            _lib.check(lib.des_cma_rank_mu_tc(_ptr(out, torch.float32, 'out'), _ptr(Y, torch.float32, 'Y'),
+                                              _ptr(w, torch.float32, 'w'), lam, n, 1 if packed else 0,
+                                              C.c_void_p(ws.data_ptr()), ws.numel(), _stream()), 'des_cma_rank_mu_tc')
+        elif packed:
+            _lib.check(lib.des_cma_rank_mu_packed(_ptr(out, torch.float32, 'out'), _ptr(Y, torch.float32, 'Y'),
+                                                  _ptr(w, torch.float32, 'w'), lam, n, _stream()), 'des_cma_rank_mu_packed')
+        else:
+            _lib.check(lib.des_cma_rank_mu(_ptr(out, torch.float32, 'out'), _ptr(Y, torch.float32, 'Y'),
+                                           _ptr(w, torch.float32, 'w'), lam, n, _stream()), 'des_cma_rank_mu')
+    return out
+
+
+def cma_rank_mu(Y, w, out=None, path=None):
+    """dC[n,n] = sum_i w_i y_i y_i^T for Y[lambda_local, n] (rank-mu term of es.tell, cma_es.py:90).
+    path: None = tensor cores (split-fp16 tcgen05 SYRK) for n >= 256, fp32 FFMA below; 'tc' / 'ffma' force one."""
     lam, n = Y.shape
     if w.numel() != lam:
         raise RuntimeError('w has %d entries, Y has %d rows' % (w.numel(), lam))
     if out is None:
         out = torch.empty((n, n), dtype=torch.float32, device=Y.device)
-    with _on(Y, 'Y'):
-        _lib.check(_lib.load().des_cma_rank_mu(_ptr(out, torch.float32, 'out'), _ptr(Y, torch.float32, 'Y'),
-                                               _ptr(w, torch.float32, 'w'), lam, n, _stream()), 'des_cma_rank_mu')
-    return out
+    return _cma_rank_mu(Y, w, out, False, path)
 
 
 def cma_cov_apply(Cmat, dC, pc, *, decay, c1, cmu):
@@ -289,17 +321,14 @@ def cma_packed_elems(n):
     return int(_lib.load().des_cma_packed_elems(int(n)))
 
 
-def cma_rank_mu_packed(Y, w, out=None):
+def cma_rank_mu_packed(Y, w, out=None, path=None):
     """The rank-mu partial as packed upper-triangular tiles (the multi-GPU all-reduce payload: half of [n, n])."""
     lam, n = Y.shape
     if w.numel() != lam:
         raise RuntimeError('w has %d entries, Y has %d rows' % (w.numel(), lam))
     if out is None:
         out = torch.empty(cma_packed_elems(n), dtype=torch.float32, device=Y.device)
-    with _on(Y, 'Y'):
-        _lib.check(_lib.load().des_cma_rank_mu_packed(_ptr(out, torch.float32, 'out'), _ptr(Y, torch.float32, 'Y'),
-                                                      _ptr(w, torch.float32, 'w'), lam, n, _stream()), 'des_cma_rank_mu_packed')
-    return out
+    return _cma_rank_mu(Y, w, out, True, path)
 
 
 def cma_cov_apply_packed(Cmat, tiles, pc, *, decay, c1, cmu):

@@ -237,6 +237,14 @@ DES_API int des_cma_rank_mu_packed(float *tiles_out_dev, const float *Y_dev, con
 DES_API int des_cma_cov_apply_packed(float *C_dev, const float *tiles_dev, const float *pc_dev, int64_t n, double decay,
                                      double c1, double cmu, void *stream);
 
+/* The rank-mu term on the tensor cores (csrc/des_cma_tc.cu): dC = Zs^T Z with Z = diag(sqrt|w|) Y, operands split into
+ * fp16 hi + lo (three tcgen05 MMAs per k-step, fp32 accumulation, TMA-fed) — same result contract as des_cma_rank_mu
+ * (packed == 0: full symmetric [n][n]) / des_cma_rank_mu_packed (packed != 0), within 1e-5 of the fp64 restatement in both
+ * norms.  Needs des_cma_tc_workspace_bytes(n, lambda_local) bytes of workspace; |sqrt|w_k| * y| must stay below 65504. */
+DES_API size_t des_cma_tc_workspace_bytes(int64_t n, int64_t lambda_local);
+DES_API int des_cma_rank_mu_tc(float *out_dev, const float *Y_dev, const float *w_dev, int64_t lambda_local, int64_t n,
+                               int packed, void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* ---- exchange steps of a sharded generation over peer memory (NVLink) ------------------------- */
 
 /* One process per GPU on one node.  Replaces the reference's result pipe (natural_es.py:62-75: every worker ships
