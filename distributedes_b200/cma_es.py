@@ -80,6 +80,9 @@ class CMAEvolutionStrategy:
         self.D = torch.ones(self.n, dtype=f64, device=dev)
         self.gen = 0
         self.chiN = np.sqrt(self.n) * (1 - 1.0 / (4 * self.n) + 1.0 / (21 * self.n * self.n))
+        # lazy eigendecomposition (tutorial, reference code B.2): B, D are refreshed every 1/((c1+cmu) n 10) generations,
+        # at least every generation — which is what lambda ~ n/4 gives at BASELINE configs[2] and [4]
+        self.eigen_gap = max(1, int(1.0 / ((k['c1'] + k['cmu']) * self.n * 10.0)))
 
     def ask(self, z=None):
         """The rank's solutions x_i = m + sigma*B*D*z_i, i in [offset, offset + n_local) (cma_es.py:62; all lambda of
@@ -161,9 +164,10 @@ class CMAEvolutionStrategy:
         else:
             self.kn.cma_cov_apply(self.C, self.dC, pc32, decay=decay, c1=c1, cmu=cmu)
         self.sigma = self.sigma * float(np.exp((cs / ds) * (norm_ps / self.chiN - 1)))
-        d2, self.B = torch.linalg.eigh(self.C.to(torch.float64))            # library eigendecomposition (cuSOLVER)
-        self.D = torch.sqrt(torch.clamp(d2, min=1e-300))
         self.gen += 1
+        if self.gen % self.eigen_gap == 0:
+            d2, self.B = torch.linalg.eigh(self.C.to(torch.float64))        # library eigendecomposition (cuSOLVER)
+            self.D = torch.sqrt(torch.clamp(d2, min=1e-300))
         return order
 
 

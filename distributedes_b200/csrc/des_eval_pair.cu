@@ -146,6 +146,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
 // tanh(v + b) for four activations, biases pre-scaled by 2 log2(e): e = 2^min(v c + b c, 30), d = 1 + e,
 // 1/d_i from ONE reciprocal of d0 d1 d2 d3 and partial products; t = 1 - 2/d.   abs err ~3e-7.
 __device__ __forceinline__ void tanh4(float2 v01, float2 v23, float4 bs, float2 &t01, float2 &t23) {
+#ifdef DES_PAIR_PLAIN_RCP
+    t01 = tanh_acc2(v01, make_float2(bs.x, bs.y));      // experiment: one reciprocal per activation (2 MUFU, 3.5 issue slots)
+    t23 = tanh_acc2(v23, make_float2(bs.z, bs.w));
+    return;
+#endif
     const float2 c = make_float2(kTwoLog2e, kTwoLog2e);
     float2 a01 = ffma2(v01, c, make_float2(bs.x, bs.y));
     float2 a23 = ffma2(v23, c, make_float2(bs.z, bs.w));
@@ -199,7 +204,7 @@ __device__ __forceinline__ void store_octet(uint8_t *slot, int r, int c8, const 
     if (X3) *reinterpret_cast<uint4 *>(slot + 8192 + off) = lo;
 }
 
-template <int H, bool X3>
+template <int H, bool X3, int A4>
 __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_constant__ CUtensorMap w2_map) {
     using C = Cfg<H, X3>;
     const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
@@ -209,11 +214,21 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
     uint8_t *ring = xs + C::X_TILE_BYTES;                                  // n_slots * SLOT_BYTES
     uint8_t *th_stage = ring + (size_t)a.n_slots * C::SLOT_BYTES;          // kThStages x 16 KB TMA destinations
     float *small1 = reinterpret_cast<float *>(th_stage + kThStages * kThetaStage); // [2][H]: b1' * 2log2e
-    const int s2_floats = H + a.a4 * H + kMaxA;                            // b2' * 2log2e | W3' [a4][H] | b3'[8]
+    const int s2_floats = H + A4 * H + kMaxA;                            // b2' * 2log2e | W3' [a4][H] | b3'[8]
     float *small2 = small1 + 2 * H;                                        // [2][s2_floats]
     Bars *bars = reinterpret_cast<Bars *>((reinterpret_cast<uintptr_t>(small2 + 2 * s2_floats) + 15) & ~(uintptr_t)15);
     // action partial sums handed from the odd-group warp to the even-group warp of a quadrant: [2][128 rows][a4]
     float *act_x = reinterpret_cast<float *>(bars + 1);
+    // member-independent theta the generators add their noise to, resident for the whole kernel (round-2 trace: the
+    // __ldg latency of these small pieces sat on the slowest generator warps' critical path every member):
+    //   W1 rows of this CTA [NCH*64][d0p] | b1 [H] | b2 [H] | W3 [A][H] | b3 [A -> 4-padded]
+    const int d0p = (a.L.d0 + 3) & ~3;
+    float *th_w1 = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(act_x + 2 * 128 * A4) + 15) & ~(uintptr_t)15);
+    float *th_b1 = th_w1 + C::NCH * 64 * d0p;
+    float *th_b2 = th_b1 + H;
+    float *th_w3 = th_b2 + H;
+    float *th_b3 = th_w3 + A4 * H;
+    float *tgt_s = th_b3 + kMaxA;                                          // this CTA's 128 target rows [128][A4]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const Layout L = a.L;
@@ -265,6 +280,21 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
     }
     // unused action rows of W3' stay zero (finite) in both buffers
     for (int i = threadIdx.x; i < 2 * s2_floats; i += blockDim.x) small2[i] = 0.f;
+    for (int i = threadIdx.x; i < C::NCH * 64 * d0p; i += blockDim.x) {
+        const int lr = i / d0p, k = i - lr * d0p;                       // local row = nc*64 + r  ->  W1 row nc*128 + 64 rank + r
+        const int n = (lr >> 6) * kNC + 64 * (int)rank + (lr & 63);
+        th_w1[i] = k < L.d0 ? __ldg(a.theta + L.off_w1 + n * L.d0 + k) : 0.f;
+    }
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        th_b1[i] = __ldg(a.theta + L.off_b1 + i);
+        th_b2[i] = __ldg(a.theta + L.off_b2 + i);
+    }
+    for (int i = threadIdx.x; i < A4 * H; i += blockDim.x) th_w3[i] = i < L.A * H ? __ldg(a.theta + L.off_w3 + i) : 0.f;
+    if (threadIdx.x < kMaxA) th_b3[threadIdx.x] = (int)threadIdx.x < L.A ? __ldg(a.theta + L.off_b3 + threadIdx.x) : 0.f;
+    for (int i = threadIdx.x; i < 128 * A4; i += blockDim.x) {
+        const int r = i / A4, q = i - r * A4;
+        tgt_s[i] = q < L.A ? __ldg(a.target + (int64_t)((int)rank * 128 + r) * L.A + q) : 0.f;
+    }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -434,7 +464,7 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
             if (lane == 0) mbar_arrive(smem_u32(&bars->s1_empty[p]));
         };
 
-        float2 actp[kMaxA];                          // (even-n, odd-n) partial sums of action q
+        float2 actp[A4];                          // (even-n, odd-n) partial sums of action q
         // ---------------- E2 chunk nc: H2 = tanh(D2 + b2'); a += H2 W3'^T in fp32 registers
         auto epilogue2 = [&](uint32_t p, int nc, int64_t tri) {
             const uint32_t u = acc_u++, st = u & 1, ph = (u >> 1) & 1;
@@ -476,12 +506,10 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                         }
                         // layer 3 (model.py:38) in fp32 on packed FFMA2: W3' row-major [q][n], 4 consecutive n per LDS.128
 #pragma unroll
-                        for (int q = 0; q < kMaxA; ++q) {
-                            if (q < 4 || a.a4 > 4) {
-                                const float4 w = lds128(w3 + (q * H + n0) * 4);
-                                actp[q] = ffma2(h01, make_float2(w.x, w.y), actp[q]);
-                                actp[q] = ffma2(h23, make_float2(w.z, w.w), actp[q]);
-                            }
+                        for (int q = 0; q < A4; ++q) {
+                            const float4 w = lds128(w3 + (q * H + n0) * 4);
+                            actp[q] = ffma2(h01, make_float2(w.x, w.y), actp[q]);
+                            actp[q] = ffma2(h23, make_float2(w.z, w.w), actp[q]);
                         }
                     }
                     if (gi == 0) tmem_ld16(acc_base + 32 * (2 + par) + 16 * hf, hf ? vb : va);     // next group
@@ -498,32 +526,30 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
             mbar_wait(smem_u32(&bars->s2_full[p]), (mi >> 1) & 1);
             if (ew == 0 && lane == 0) TRACE(1, i, 10);
 #pragma unroll
-            for (int q = 0; q < kMaxA; ++q) actp[q] = make_float2(0.f, 0.f);
+            for (int q = 0; q < A4; ++q) actp[q] = make_float2(0.f, 0.f);
             for (int nc = 0; nc < C::NCH - 1; ++nc) epilogue2(p, nc, i);
             if (i + 1 < n_mine) epilogue1(mi + 1);              // the next member's H1, ahead of this member's last chunk
             epilogue2(p, C::NCH - 1, i);
             // ---- member done: combine the two warps of the quadrant, clip, squared error (utils.py:134-137)
-            float act[kMaxA];
+            float act[A4];
 #pragma unroll
-            for (int q = 0; q < kMaxA; ++q) act[q] = actp[q].x + actp[q].y;
+            for (int q = 0; q < A4; ++q) act[q] = actp[q].x + actp[q].y;
             float sq = 0.f;
             if (par == 1) {
 #pragma unroll
-                for (int q = 0; q < kMaxA; ++q)
-                    if (q < a.a4) act_x[(p * 128 + row) * a.a4 + q] = act[q];
+                for (int q = 0; q < A4; ++q) act_x[(p * 128 + row) * A4 + q] = act[q];
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars->s2_empty[p]));     // done with this member's b2/W3
                 asm volatile("bar.arrive %0, 256;" ::"r"(2 + p) : "memory");     // ids alternate with the member parity
             } else {
                 asm volatile("bar.sync %0, 256;" ::"r"(2 + p) : "memory");
-                const uint32_t b3 = s2_addr + p * (uint32_t)(s2_floats * 4) + (uint32_t)((H + a.a4 * H) * 4);
-                const int t = (int)rank * 128 + row;
+                const uint32_t b3 = s2_addr + p * (uint32_t)(s2_floats * 4) + (uint32_t)((H + A4 * H) * 4);
 #pragma unroll
-                for (int q = 0; q < kMaxA; ++q) {
+                for (int q = 0; q < A4; ++q) {
                     if (q < L.A) {
-                        float v = (act[q] + act_x[(p * 128 + row) * a.a4 + q]) + lds32(b3 + q * 4);     // fixed order: even + odd groups
+                        float v = (act[q] + act_x[(p * 128 + row) * A4 + q]) + lds32(b3 + q * 4);     // fixed order: even + odd groups
                         v = fminf(fmaxf(v, -a.clip), a.clip);
-                        const float d = v - __ldg(a.target + (int64_t)t * L.A + q);
+                        const float d = v - tgt_s[row * A4 + q];
                         sq = __fmaf_rn(d, d, sq);
                     }
                 }
@@ -555,18 +581,28 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
         const int r2 = gtid >> 3, c82 = gtid & 7;
         const int row_base = 64 * (int)rank;                            // this CTA's 64 rows of every 128-row chunk
         uint32_t tq = 0;                                                // layer-2 slots generated so far (theta stage = tq % kThStages)
+        // resident theta through 32-bit shared addresses (one register) instead of five generic pointers
+        const uint32_t th_base = smem_u32(th_w1);
+        const uint32_t th_b1_off = (uint32_t)(C::NCH * 64 * d0p * 4);
         const float bsc = X3 ? kTwoLog2e : 1.0f;     // the f16x3 epilogue evaluates tanh(v + b) as 1 - 2/(1 + 2^(v c + b c))
         uint32_t mi = 0;
         for (int64_t i = 0; i < n_mine; ++i, ++mi) {
             const uint32_t member = (uint32_t)(a.member_offset + (uint64_t)(first + i * stride));
             const uint32_t p = mi & 1;
             if (gtid == 0) TRACE(2, i, 0);
+            // The small pieces are dealt to DIFFERENT warps (round-2 trace: with everything on the low thread ids, warps 0-1
+            // carried ~13 octet-equivalents per member against 8 for warps 8-15, and the slot barriers wait for the slowest):
+            //   layer-1 tile of chunk nc -> the half of the threads with (gtid >> 8) == (nc & 1);   W3' -> threads 0..A*H/4
+            //   b1' -> warps 8..;   b2' -> warps 10..;   b3' -> warp 12.   Their theta comes from the resident copy.
             // ---- b1' (needed first)
             mbar_wait(smem_u32(&bars->s1_empty[p]), ((mi >> 1) & 1) ^ 1);
-            for (int k = gtid; k < H / 4; k += kGenThreads) {
-                const float4 v1 = perturbed_quad((uint32_t)((L.off_b1 >> 2) + k), member, gen, kStreamNesEps, a.key,
-                                                 a.neg2ln2_sigma2, __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_b1) + k));
-                reinterpret_cast<float4 *>(small1 + p * H)[k] = make_float4(v1.x * bsc, v1.y * bsc, v1.z * bsc, v1.w * bsc);
+            {
+                const int k = gtid - 256;
+                if (k >= 0 && k < H / 4) {
+                    const float4 v1 = perturbed_quad((uint32_t)((L.off_b1 >> 2) + k), member, gen, kStreamNesEps, a.key,
+                                                     a.neg2ln2_sigma2, lds128(th_base + th_b1_off + (uint32_t)k * 16));
+                    reinterpret_cast<float4 *>(small1 + p * H)[k] = make_float4(v1.x * bsc, v1.y * bsc, v1.z * bsc, v1.w * bsc);
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars->s1_full[p]));
@@ -576,9 +612,10 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                 if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
                 mbar_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
                 uint8_t *slot = ring + (size_t)s * C::SLOT_BYTES;
-                if (gtid < 256) {   // 64 rows x 4 octets = 256 items
-                    const int r = gtid >> 2, c8 = gtid & 3;
+                if ((gtid >> 8) == (nc & 1)) {   // 64 rows x 4 octets = 256 items
+                    const int lt = gtid & 255, r = lt >> 2, c8 = lt & 3;
                     const int n = nc * kNC + row_base + r;
+                    const uint32_t trow = th_base + (uint32_t)((nc * 64 + r) * d0p * 4);
                     float w[8];
                     if ((L.d0 & 3) == 0) {                                // row starts are quad aligned
 #pragma unroll
@@ -588,7 +625,7 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                             if (k < L.d0) {
                                 const int j = L.off_w1 + n * L.d0 + k;
                                 v = perturbed_quad((uint32_t)(j >> 2), member, gen, kStreamNesEps, a.key, a.neg2ln2_sigma2,
-                                                   __ldg(reinterpret_cast<const float4 *>(a.theta + j)));
+                                                   lds128(trow + (uint32_t)k * 4));
                             }
                             w[4 * hq] = v.x; w[4 * hq + 1] = v.y; w[4 * hq + 2] = v.z; w[4 * hq + 3] = v.w;
                         }
@@ -602,7 +639,7 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                                 const float4 z = noise_quad((uint32_t)(j >> 2), member, gen, kStreamNesEps, a.key);
                                 const int el = j & 3;
                                 const float zz = el == 0 ? z.x : (el == 1 ? z.y : (el == 2 ? z.z : z.w));
-                                x = __fmaf_rn(a.sigma, zz, __ldg(a.theta + j));
+                                x = __fmaf_rn(a.sigma, zz, lds32(trow + (uint32_t)k * 4));
                             }
                             w[e] = x;
                         }
@@ -637,7 +674,11 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                                         __fmaf_rn(pb.nr, pb.c, t0.z), __fmaf_rn(pb.nr, pb.s, t0.w),
                                         __fmaf_rn(pc.nr, pc.c, t1.x), __fmaf_rn(pc.nr, pc.s, t1.y),
                                         __fmaf_rn(pd.nr, pd.c, t1.z), __fmaf_rn(pd.nr, pd.s, t1.w)};
+#ifdef DES_PAIR_GEN_BACKOFF
+                    mbar_wait_relaxed(smem_u32(&bars->slot_empty[s]), sph ^ 1);
+#else
                     mbar_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
+#endif
                     store_octet<X3>(ring + (size_t)s * C::SLOT_BYTES, r2, c82, w);
                     fence_proxy_async_smem();
                     __syncwarp();
@@ -648,21 +689,25 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                     // ---- b2', W3', b3': needed by the epilogue of layer 2, i.e. once the first output chunk has left the tensor pipe
                     mbar_wait(smem_u32(&bars->s2_empty[p]), ((mi >> 1) & 1) ^ 1);
                     float *sm2 = small2 + p * s2_floats;
-                    for (int k = gtid; k < H / 4; k += kGenThreads) {
-                        const float4 v2 = perturbed_quad((uint32_t)((L.off_b2 >> 2) + k), member, gen, kStreamNesEps, a.key,
-                                                         a.neg2ln2_sigma2, __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_b2) + k));
-                        reinterpret_cast<float4 *>(sm2)[k] = make_float4(v2.x * bsc, v2.y * bsc, v2.z * bsc, v2.w * bsc);
-                    }
-                    for (int k = gtid; k < L.A * H / 4; k += kGenThreads)            // W3' [q][n] row-major: aligned quads
-                        reinterpret_cast<float4 *>(sm2 + H)[k] =
-                            perturbed_quad((uint32_t)((L.off_w3 >> 2) + k), member, gen, kStreamNesEps, a.key, a.neg2ln2_sigma2,
-                                           __ldg(reinterpret_cast<const float4 *>(a.theta + L.off_w3) + k));
-                    if (gtid < L.A) {
-                        const int j = L.off_b3 + gtid;
-                        const float4 z = noise_quad((uint32_t)(j >> 2), member, gen, kStreamNesEps, a.key);
-                        const int el = j & 3;
-                        const float zz = el == 0 ? z.x : (el == 1 ? z.y : (el == 2 ? z.z : z.w));
-                        sm2[H + a.a4 * H + gtid] = __fmaf_rn(a.sigma, zz, __ldg(a.theta + j));
+                    if (gtid < L.A * H / 4)                                   // W3' [q][n] row-major: aligned quads
+                        reinterpret_cast<float4 *>(sm2 + H)[gtid] =
+                            perturbed_quad((uint32_t)((L.off_w3 >> 2) + gtid), member, gen, kStreamNesEps, a.key, a.neg2ln2_sigma2,
+                                           lds128(th_base + th_b1_off + (uint32_t)(2 * H * 4) + (uint32_t)gtid * 16));
+                    {
+                        const int k = gtid - 320;
+                        if (k >= 0 && k < H / 4) {
+                            const float4 v2 = perturbed_quad((uint32_t)((L.off_b2 >> 2) + k), member, gen, kStreamNesEps, a.key,
+                                                             a.neg2ln2_sigma2, lds128(th_base + th_b1_off + (uint32_t)(H * 4) + (uint32_t)k * 16));
+                            reinterpret_cast<float4 *>(sm2)[k] = make_float4(v2.x * bsc, v2.y * bsc, v2.z * bsc, v2.w * bsc);
+                        }
+                        const int q = gtid - 384;
+                        if (q >= 0 && q < L.A) {
+                            const int jj = L.off_b3 + q;
+                            const float4 z = noise_quad((uint32_t)(jj >> 2), member, gen, kStreamNesEps, a.key);
+                            const int el = jj & 3;
+                            const float zz = el == 0 ? z.x : (el == 1 ? z.y : (el == 2 ? z.z : z.w));
+                            sm2[H + A4 * H + q] = __fmaf_rn(a.sigma, zz, lds32(th_base + th_b1_off + (uint32_t)((2 * H + A4 * H + q) * 4)));
+                        }
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&bars->s2_full[p]));
@@ -695,7 +740,7 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-template <int H, bool X3>
+template <int H, bool X3, int A4>
 static int launch(Args &a, cudaStream_t st) {
     using C = Cfg<H, X3>;
     // tensor map of fc2.weight: [H rows][H columns] fp32 inside theta, boxes of 64 x 64
@@ -716,10 +761,11 @@ static int launch(Args &a, cudaStream_t st) {
         set_error("des_nes_eval(tensor): cuTensorMapEncodeTiled failed (%d)", (int)cr);
         return DES_ERR_CUDA;
     }
-    a.a4 = a.L.A > 4 ? 8 : 4;
+    a.a4 = A4;
     const size_t s2_floats = (size_t)H + (size_t)a.a4 * H + kMaxA;
     const size_t fixed = 1024 + C::X_TILE_BYTES + kThStages * kThetaStage + (2 * H + 2 * s2_floats) * sizeof(float) + 16 + sizeof(Bars) +
-                         2 * 128 * (size_t)a.a4 * sizeof(float);
+                         2 * 128 * (size_t)a.a4 * sizeof(float) +
+                         16 + ((size_t)C::NCH * 64 * ((a.L.d0 + 3) & ~3) + 2 * H + (size_t)A4 * H + kMaxA + 128 * A4) * sizeof(float);
     int n_slots = (int)((227 * 1024 - fixed) / C::SLOT_BYTES);
     if (n_slots > 16) n_slots = 16;
     if (n_slots < 4) {
@@ -731,7 +777,7 @@ static int launch(Args &a, cudaStream_t st) {
     int dev = 0, sms = 148;
     DES_CUDA(cudaGetDevice(&dev));
     DES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    DES_CUDA(cudaFuncSetAttribute(eval_pair_kernel<H, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DES_CUDA(cudaFuncSetAttribute(eval_pair_kernel<H, X3, A4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // each pair accumulates its two halves into the output with atomicAdd: zero it first
     DES_CUDA(cudaMemsetAsync(a.fitness, 0, (size_t)a.n_local * sizeof(float), st));
     const int64_t pairs = a.n_local < sms / 2 ? a.n_local : sms / 2;
@@ -756,7 +802,7 @@ static int launch(Args &a, cudaStream_t st) {
 #else
     a.trace = nullptr;
 #endif
-    DES_CUDA(cudaLaunchKernelEx(&cfg, eval_pair_kernel<H, X3>, a, map));
+    DES_CUDA(cudaLaunchKernelEx(&cfg, eval_pair_kernel<H, X3, A4>, a, map));
     DES_LAUNCH_CHECK("eval_pair_kernel");
 #ifdef DES_PAIR_TRACE
     if (a.trace) {        // debug builds only: synchronous dump of the stamps (cycles relative to the first one)
@@ -806,7 +852,9 @@ int eval_pair_launch(float *fitness, const float *theta, const float *obs, const
     a.key = make_philox_key(seed); a.gen = (uint32_t)generation;
     a.member_offset = (uint64_t)member_offset; a.n_local = n_local;
     (void)precision;
-    return dims.hidden == 256 ? launch<256, true>(a, st) : launch<128, true>(a, st);
+    const bool wide = dims.action_dim > 4;
+    if (dims.hidden == 256) return wide ? launch<256, true, 8>(a, st) : launch<256, true, 4>(a, st);
+    return wide ? launch<128, true, 8>(a, st) : launch<128, true, 4>(a, st);
 }
 
 }  // namespace des

@@ -70,21 +70,23 @@ __global__ void rank_finish_kernel(float *__restrict__ shaped, int32_t *__restri
 //   4. members are grouped by bucket (order inside a bucket is arbitrary; it does not matter below)
 //   5. rank_i = bucket_start + #{j in bucket : (key_j, j) < (key_i, i)}     — exact, ties by index
 // Degenerate inputs (all keys equal) put everything in one bucket: still exact, cost falls back to n * N.
-constexpr int kBuckets = 1024;
-constexpr int kSamples = 4096;
+constexpr int kBuckets = 1024;          // upper bound; populations up to 256k use 256 buckets / 1024 samples (the sample
+constexpr int kSamples = 4096;          // sort is a single CTA: 36 us at 4096 samples, the largest piece of the rank path)
 constexpr int64_t kBucketMinN = 8192;
+__host__ __device__ inline int buckets_for(int64_t N) { return N <= 262144 ? 256 : kBuckets; }
 
 __global__ void __launch_bounds__(1024) rank_splitters_kernel(uint32_t *__restrict__ splitters,
-                                                              const float *__restrict__ fitness, int64_t N) {
+                                                              const float *__restrict__ fitness, int64_t N, int nb) {
     __shared__ uint32_t sk[kSamples];
-    for (int t = threadIdx.x; t < kSamples; t += 1024) {
-        const int64_t j = (int64_t)(((unsigned __int128)t * (unsigned __int128)N) / kSamples);
+    const int ns = 4 * nb;                   // samples
+    for (int t = threadIdx.x; t < ns; t += 1024) {
+        const int64_t j = (int64_t)(((unsigned __int128)t * (unsigned __int128)N) / ns);
         sk[t] = order_key(__ldg(fitness + j));
     }
     __syncthreads();
-    for (int k = 2; k <= kSamples; k <<= 1) {
+    for (int k = 2; k <= ns; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < kSamples; t += 1024) {
+            for (int t = threadIdx.x; t < ns; t += 1024) {
                 const int p = t ^ j;
                 if (p > t) {
                     const uint32_t a = sk[t], b = sk[p];
@@ -95,12 +97,12 @@ __global__ void __launch_bounds__(1024) rank_splitters_kernel(uint32_t *__restri
             __syncthreads();
         }
     }
-    for (int t = threadIdx.x; t < kBuckets - 1; t += 1024) splitters[t] = sk[(t + 1) * (kSamples / kBuckets)];
+    for (int t = threadIdx.x; t < nb - 1; t += 1024) splitters[t] = sk[(t + 1) * 4];
 }
 
 // bucket(key) = #{splitters <= key}  (monotone in key, so bucket order == key order)
-__device__ __forceinline__ int bucket_of_key(const uint32_t *sp, uint32_t key) {
-    int lo = 0, hi = kBuckets - 1;            // answer in [0, kBuckets-1]
+__device__ __forceinline__ int bucket_of_key(const uint32_t *sp, uint32_t key, int nb) {
+    int lo = 0, hi = nb - 1;                  // answer in [0, nb-1]
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (sp[mid] <= key) lo = mid + 1; else hi = mid;
@@ -111,14 +113,14 @@ __device__ __forceinline__ int bucket_of_key(const uint32_t *sp, uint32_t key) {
 __global__ void __launch_bounds__(256) rank_bucket_hist_kernel(int32_t *__restrict__ bucket_count,
                                                                uint16_t *__restrict__ bucket_id, uint32_t *__restrict__ keys,
                                                                const uint32_t *__restrict__ splitters,
-                                                               const float *__restrict__ fitness, int64_t N) {
+                                                               const float *__restrict__ fitness, int64_t N, int nb) {
     __shared__ uint32_t sp[kBuckets];
-    for (int t = threadIdx.x; t < kBuckets - 1; t += 256) sp[t] = splitters[t];
+    for (int t = threadIdx.x; t < nb - 1; t += 256) sp[t] = splitters[t];
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= N) return;
     const uint32_t key = order_key(__ldg(fitness + i));
-    const int b = bucket_of_key(sp, key);
+    const int b = bucket_of_key(sp, key, nb);
     keys[i] = key;
     bucket_id[i] = (uint16_t)b;
     atomicAdd(bucket_count + b, 1);
@@ -129,9 +131,10 @@ __global__ void __launch_bounds__(kBuckets) rank_bucket_scan_kernel(int32_t *__r
                                                                     const int32_t *__restrict__ bucket_count) {
     __shared__ int32_t s[kBuckets];
     const int t = threadIdx.x;
+    const int nbk = blockDim.x;
     s[t] = bucket_count[t];
     __syncthreads();
-    for (int o = 1; o < kBuckets; o <<= 1) {          // Hillis-Steele inclusive scan
+    for (int o = 1; o < nbk; o <<= 1) {               // Hillis-Steele inclusive scan
         const int32_t v = (t >= o) ? s[t - o] : 0;
         __syncthreads();
         s[t] += v;
@@ -233,9 +236,10 @@ extern "C" DES_API int des_centered_rank(float *shaped_out_dev, int32_t *rank_ou
         const BucketWs w = carve(workspace_dev, N);
         const unsigned gn = (unsigned)((N + 255) / 256);
         DES_CUDA(cudaMemsetAsync(w.bucket_count, 0, kBuckets * sizeof(int32_t), st));
-        rank_splitters_kernel<<<1, 1024, 0, st>>>(w.splitters, fitness_all_dev, N);
-        rank_bucket_hist_kernel<<<gn, 256, 0, st>>>(w.bucket_count, w.bucket_id, w.keys, w.splitters, fitness_all_dev, N);
-        rank_bucket_scan_kernel<<<1, kBuckets, 0, st>>>(w.bucket_start, w.bucket_fill, w.bucket_count);
+        const int nb = buckets_for(N);
+        rank_splitters_kernel<<<1, 1024, 0, st>>>(w.splitters, fitness_all_dev, N, nb);
+        rank_bucket_hist_kernel<<<gn, 256, 0, st>>>(w.bucket_count, w.bucket_id, w.keys, w.splitters, fitness_all_dev, N, nb);
+        rank_bucket_scan_kernel<<<1, nb, 0, st>>>(w.bucket_start, w.bucket_fill, w.bucket_count);
         rank_bucket_group_kernel<<<gn, 256, 0, st>>>(w.g_key, w.g_idx, w.bucket_fill, w.bucket_start, w.bucket_id, w.keys, N);
         rank_bucket_finish_kernel<<<(unsigned)((n_local + 255) / 256), 256, 0, st>>>(
             shaped_out_dev, rank_out_dev, w.g_key, w.g_idx, w.bucket_start, w.bucket_count, w.bucket_id, w.keys, N,

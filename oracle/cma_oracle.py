@@ -36,6 +36,13 @@ def cma_constants(n, lam, active=False):
     return dict(w=w, mu=mu, mu_eff=mu_eff, cc=cc, c1=c1, cmu=cmu, cs=cs, ds=ds)
 
 
+def eigen_gap(n, c1, cmu):
+    """Generations between eigendecompositions of C: the tutorial's lazy update (its reference code B.2 refreshes B, D when
+    counteval - eigeneval > lambda/(c1+cmu)/n/10, i.e. every 1/((c1+cmu) n 10) generations), at least every generation.
+    For BASELINE configs[2] (n=1024, lambda=256) and configs[4] (n=4096, lambda=1024) this is 1: lambda ~ n/4 makes cmu large."""
+    return max(1, int(1.0 / ((c1 + cmu) * n * 10.0)))
+
+
 def sort_and_scale(X, cost, m_old, sigma):
     """y_{i:lambda} = (x_{i:lambda} - m_old)/sigma, members sorted by cost ascending (eq. 41-42);
     ties by index.  (cma_es.py:89 rank-shapes the costs first; ranks preserve the order.)"""
@@ -84,6 +91,7 @@ class CMAState:
         self.D = np.ones(n)
         self.gen = 0
         self.chiN = np.sqrt(n) * (1 - 1.0 / (4 * n) + 1.0 / (21 * n * n))
+        self.gap = eigen_gap(n, self.k['c1'], self.k['cmu'])
 
     def ask(self, z):
         """x_i = m + sigma * B D z_i (eq. 38-40); z [lambda, n] standard normal."""
@@ -106,7 +114,8 @@ class CMAState:
         self.dC = dC
         self.sigma = self.sigma * np.exp((cs / ds) * (norm_ps / self.chiN - 1))               # eq. 44
         self.C = 0.5 * (self.C + self.C.T)
-        d2, self.B = np.linalg.eigh(self.C)
-        self.D = np.sqrt(np.maximum(d2, 1e-300))
         self.gen += 1
+        if self.gen % self.gap == 0:                                     # lazy eigendecomposition (tutorial B.2)
+            d2, self.B = np.linalg.eigh(self.C)
+            self.D = np.sqrt(np.maximum(d2, 1e-300))
         return order

@@ -5,13 +5,12 @@ set -e
 name=$1; src=$2; shift 2
 cd "$(dirname "$0")/.."
 python -m distributedes_b200.build > /dev/null
-obj=distributedes_b200/build/${src%.cu}_$name.o
+mkdir -p distributedes_b200/build/variants
+obj=distributedes_b200/build/variants/${src%.cu}_$name.o
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden "$@" -c distributedes_b200/csrc/$src -o $obj
-objs=$(ls distributedes_b200/build/*.o | grep -v "_[a-z0-9]*\.o$" | grep -v "${src%.cu}.o"; echo)
 others=""
 for o in distributedes_b200/build/des_*.o; do
-  b=$(basename $o .o)
-  case $b in des_capi|des_noise|des_eval_ffma|des_eval_tc|des_eval_pair|des_rank|des_update|des_cma|des_envs|des_comm) [ "$b" != "${src%.cu}" ] && others="$others $o";; esac
+  [ "$(basename $o .o)" != "${src%.cu}" ] && others="$others $o"
 done
 nvcc -shared -gencode arch=compute_100a,code=sm_100a -o distributedes_b200/libdes_b200_$name.so $others $obj
 echo distributedes_b200/libdes_b200_$name.so

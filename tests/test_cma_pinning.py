@@ -94,3 +94,25 @@ def test_product_constants_equal_oracle_constants():
         for key in ('mu', 'mu_eff', 'cc', 'c1', 'cmu', 'cs', 'ds'):
             assert a[key] == b[key], (n, lam, key)
         assert np.array_equal(a['w'], b['w'])
+
+
+def test_lazy_eigendecomposition_gap():
+    """tutorial B.2: B, D refreshed every 1/((c1+cmu) n 10) generations (>= 1).  Small lambda against n -> several
+    generations between decompositions; the BASELINE configs (lambda ~ n/4) -> every generation."""
+    k = co.cma_constants(1024, 256)
+    assert co.eigen_gap(1024, k['c1'], k['cmu']) == 1
+    k = co.cma_constants(4096, 1024)
+    assert co.eigen_gap(4096, k['c1'], k['cmu']) == 1
+    k = co.cma_constants(1000, 12)                                    # pycma's default lambda for n = 1000 is 4+floor(3 ln n) = 24
+    gap = co.eigen_gap(1000, k['c1'], k['cmu'])
+    assert gap == int(1.0 / ((k['c1'] + k['cmu']) * 1000 * 10)) and gap >= 2
+    st = co.CMAState(np.zeros(40), 1.0, 6)
+    assert st.gap >= 1
+    rs = np.random.RandomState(1)
+    B0 = st.B.copy()
+    for g in range(st.gap):
+        X = st.ask(rs.randn(6, 40))
+        st.tell(X, co.sphere(X))
+        if g + 1 < st.gap:
+            assert np.array_equal(st.B, B0)                           # untouched between refreshes
+    assert not np.array_equal(st.B, B0)
