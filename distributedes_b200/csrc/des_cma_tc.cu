@@ -13,6 +13,7 @@
 // The fp32 FFMA kernel of des_cma.cu (36 % of the CUDA-core peak in round 1) stays as the small-n / no-workspace path.
 // Accuracy: measured against the fp64 restatement in tests/test_gpu_cma.py at the same 1e-5 (both norms) bar.
 #include <cuda.h>
+#include <stddef.h>
 #include "des_common.cuh"
 #include "des_tc.cuh"
 
@@ -83,6 +84,14 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// one lane of a fully converged warp: the loop around it runs on the whole warp so that every operand of the TMA / MMA
+// instructions is warp-uniform (inside `if (lane == 0)` ptxas wraps each of them in an ELECT / R2UR.BROADCAST loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 struct Bars {
     uint64_t full[kStages], empty[kStages], acc_full;
     uint32_t tmem_base;
@@ -117,41 +126,47 @@ __global__ void __launch_bounds__(kThreads, 1) cma_syrk_kernel(Args a, const __g
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
 
+    const uint32_t smem_addr = smem_u32(smem), bars_addr = smem_u32(bars);
     if (warp == 0) {
-        if (lane == 0) {                       // ---- TMA producer
-            for (int ks = 0; ks < a.k_stages; ++ks) {
-                const int s = ks % kStages, use = ks / kStages;
-                if (use > 0) mbar_wait(smem_u32(&bars->empty[s]), (use - 1) & 1);
-                const uint32_t bar = smem_u32(&bars->full[s]);
-                const uint32_t base = smem_u32(smem + s * kStageBytes);
+        // ---- TMA producer (whole warp converged, one elected lane issues)
+        for (int ks = 0; ks < a.k_stages; ++ks) {
+            const int s = ks % kStages, use = ks / kStages;
+            if (use > 0) mbar_wait(bars_addr + (uint32_t)offsetof(Bars, empty) + 8u * s, (use - 1) & 1);
+            const uint32_t bar = bars_addr + (uint32_t)offsetof(Bars, full) + 8u * s;
+            const uint32_t base = smem_addr + (uint32_t)(s * kStageBytes);
+            if (elect_one()) {
                 mbar_expect_tx(bar, kStageBytes);
                 tma_load_2d(base, &map_a_hi, ks * kBK, bi * kBM, bar);
                 tma_load_2d(base + kABytes, &map_a_lo, ks * kBK, bi * kBM, bar);
                 tma_load_2d(base + 2 * kABytes, &map_b_hi, ks * kBK, bj * kBN, bar);
                 tma_load_2d(base + 2 * kABytes + kBBytes, &map_b_lo, ks * kBK, bj * kBN, bar);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {                       // ---- MMA issuer
-            constexpr uint32_t idesc = idesc_f16(kBM, kBN);
-            for (int ks = 0; ks < a.k_stages; ++ks) {
-                const int s = ks % kStages, use = ks / kStages;
-                mbar_wait(smem_u32(&bars->full[s]), use & 1);
-                tc_fence_after();
-                const uint32_t base = smem_u32(smem + s * kStageBytes);
+        // ---- MMA issuer (whole warp converged, one elected lane issues)
+        constexpr uint32_t idesc = idesc_f16(kBM, kBN);
+        const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+        for (int ks = 0; ks < a.k_stages; ++ks) {
+            const int s = ks % kStages, use = ks / kStages;
+            mbar_wait(bars_addr + (uint32_t)offsetof(Bars, full) + 8u * s, use & 1);
+            tc_fence_after();
+            const uint32_t base = smem_addr + (uint32_t)(s * kStageBytes);
+            if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < kBK / 16; ++k) {
                     const uint64_t ah = smem_desc_sw128(base) + (uint64_t)(k * 2);
                     const uint64_t al = smem_desc_sw128(base + kABytes) + (uint64_t)(k * 2);
                     const uint64_t bh = smem_desc_sw128(base + 2 * kABytes) + (uint64_t)(k * 2);
                     const uint64_t bl = smem_desc_sw128(base + 2 * kABytes + kBBytes) + (uint64_t)(k * 2);
-                    mma_ss(tmem, ah, bh, idesc, (ks | k) != 0);
-                    mma_ss(tmem, al, bh, idesc, 1);
-                    mma_ss(tmem, ah, bl, idesc, 1);
+                    mma_ss(tm, ah, bh, idesc, (ks | k) != 0);
+                    mma_ss(tm, al, bh, idesc, 1);
+                    mma_ss(tm, ah, bl, idesc, 1);
                 }
-                mma_commit(smem_u32(&bars->empty[s]));
+                mma_commit(bars_addr + (uint32_t)offsetof(Bars, empty) + 8u * s);
+                if (ks == a.k_stages - 1) mma_commit(bars_addr + (uint32_t)offsetof(Bars, acc_full));
             }
-            mma_commit(smem_u32(&bars->acc_full));
+            __syncwarp();
         }
     } else {
         // ---- epilogue: TMEM lane quadrant = warp id % 4; lane = output row

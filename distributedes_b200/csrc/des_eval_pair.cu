@@ -47,8 +47,13 @@ using namespace tc;
 
 namespace pairk {
 
-constexpr int kGenWarps = 16;
+#ifndef DES_PAIR_GEN_WARPS
+#define DES_PAIR_GEN_WARPS 16
+#endif
+constexpr int kGenWarps = DES_PAIR_GEN_WARPS;          // 16 (one octet of a layer-2 tile per thread) or 8 (two, interleaved)
 constexpr int kGenThreads = kGenWarps * 32;
+constexpr int kOct = 512 / kGenThreads;                // octets of a 64 x 64 tile per generator thread
+static_assert(kGenWarps == 16 || kGenWarps == 8, "generator warps: 16 or 8");
 constexpr int kEpiWarps = 8;
 constexpr int kMmaWarp = kGenWarps;            // warpgroup 4: MMA issuer, TMA producer, two idle warps
 constexpr int kProdWarp = kMmaWarp + 1;
@@ -65,6 +70,19 @@ constexpr int kThStages = DES_PAIR_THETA_STAGES;
 // Register budget: the kernel is launched with kLaunchRegs per thread (__maxnreg__), i.e. a pool of 896 x 72 = 64 512;
 // setmaxnreg then moves registers from the generators to the epilogue warps.  The sum must fit the pool, or the
 // epilogue's setmaxnreg.inc never returns.
+#if DES_PAIR_GEN_WARPS == 8        // 20 warps: launched with 96 registers per thread (pool 61 440)
+#define DES_PAIR_LAUNCH_REGS 96
+#ifndef DES_PAIR_GEN_REGS
+#define DES_PAIR_GEN_REGS 96
+#endif
+#ifndef DES_PAIR_EPI_REGS
+#define DES_PAIR_EPI_REGS 112
+#endif
+#ifndef DES_PAIR_MMA_REGS
+#define DES_PAIR_MMA_REGS 56
+#endif
+#else                             // 28 warps: launched with 72 (pool 64 512)
+#define DES_PAIR_LAUNCH_REGS 72
 #ifndef DES_PAIR_GEN_REGS
 #define DES_PAIR_GEN_REGS 56
 #endif
@@ -74,7 +92,13 @@ constexpr int kThStages = DES_PAIR_THETA_STAGES;
 #ifndef DES_PAIR_MMA_REGS
 #define DES_PAIR_MMA_REGS 72      // warpgroup 4 keeps its launch allocation (no setmaxnreg)
 #endif
-constexpr int kLaunchRegs = 72;     // 28 warps x 32 x 72 = 64 512 <= 65 536
+#endif
+#ifdef DES_PAIR_UNBALANCED      // experiment: all the small pieces on the low thread ids (round-2 v4 assignment)
+constexpr int kB1Off = 0, kB2Off = 0, kB3Off = 0, kL1Alt = 0;
+#else
+constexpr int kB1Off = kGenThreads / 2, kB2Off = kGenThreads / 2 + 64, kB3Off = kGenWarps == 16 ? kGenThreads / 2 + 128 : 0, kL1Alt = kGenWarps == 16 ? 1 : 0;
+#endif
+constexpr int kLaunchRegs = DES_PAIR_LAUNCH_REGS;
 constexpr int kGenRegs = DES_PAIR_GEN_REGS, kEpiRegs = DES_PAIR_EPI_REGS, kMmaRegs = DES_PAIR_MMA_REGS;
 static_assert(kGenWarps * 32 * kGenRegs + kEpiWarps * 32 * kEpiRegs + 4 * 32 * kMmaRegs <= kThreads * kLaunchRegs,
               "setmaxnreg budget exceeds the registers the CTA is launched with");
@@ -184,6 +208,13 @@ constexpr int kTrFirst = 16, kTrMembers = 8, kTrEvents = 16;      // members (pe
 #else
 #define TRACE(role, i, ev) do { } while (0)
 #endif
+
+// one lane of a fully converged warp (the issuing lane of the MMA role)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 
 template <int REGS>
 __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
@@ -315,70 +346,83 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
         if (warp >= kMmaWarp && warp < kEpiWarp0) reg_dealloc<kMmaRegs>();
     }
     if (warp == kMmaWarp) {
-        if (lane == 0 && rank == 0) {
-            // =================================== MMA issuer (one thread of the leader) ===================================
+        if (rank == 0) {
+            // =================================== MMA issuer (leader CTA) ===================================
+            // The WHOLE warp runs this loop converged and one elected lane issues: every operand is then warp-uniform and
+            // lives in uniform registers.  (Round 2 trace: with the loop inside `if (lane == 0)` ptxas wrapped each
+            // tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop — ~11 dependent instructions, 160 cycles per MMA
+            // against the 64 the tensor pipe needs: the issuing thread was the bottleneck of the whole pair.)
             constexpr uint32_t idesc = idesc_f16(256, kNC);
+            const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
             uint32_t rs = 0, rph = 0;            // ring cursor: slot index and phase
             uint32_t acc_u = 0;                  // accumulator-stage use counter
             const uint32_t xaddr = smem_u32(xs);
+            const uint32_t ring_addr = smem_u32(ring), bars_addr = smem_u32(bars);
+            auto bar_of = [&](const void *field) { return bars_addr + (uint32_t)((const uint8_t *)field - (const uint8_t *)bars); };
             for (int64_t i = 0; i < n_mine; ++i) {
-                TRACE(0, i, 0);
+                if (lane == 0) TRACE(0, i, 0);
                 // ---- layer 1: D1 chunk nc = X W1'[128nc:128nc+128, :]^T, into the H1 columns (in-order after layer 2 of
                 //      the previous member, which read them)
                 for (int nc = 0; nc < C::NCH; ++nc) {
                     const uint32_t s = rs, sph = rph;
                     if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
-                    mbar_wait(smem_u32(&bars->slot_full[s]), sph);
+                    mbar_wait(bar_of(&bars->slot_full[s]), sph);
                     tc_fence_after();
-                    const uint32_t bbase = smem_u32(ring + (size_t)s * C::SLOT_BYTES);
-                    const uint32_t d = tmem + (uint32_t)(nc * kNC);
+                    const uint32_t bbase = ring_addr + s * (uint32_t)C::SLOT_BYTES;
+                    const uint32_t d = tm + (uint32_t)(nc * kNC);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < kK1 / 16; ++ks) {
-                        const uint64_t ah = smem_desc_sw128(xaddr) + (uint64_t)(ks * 2);
-                        const uint64_t bh = smem_desc_sw128(bbase) + (uint64_t)(ks * 2);
-                        mma2_f16_ss(d, ah, bh, idesc, ks > 0);
-                        if (X3) {
-                            const uint64_t al = smem_desc_sw128(xaddr + 16384) + (uint64_t)(ks * 2);
-                            const uint64_t bl = smem_desc_sw128(bbase + 8192) + (uint64_t)(ks * 2);
-                            mma2_f16_ss(d, al, bh, idesc, 1);       // X_lo W_hi
-                            mma2_f16_ss(d, ah, bl, idesc, 1);       // X_hi W_lo
+                        for (int ks = 0; ks < kK1 / 16; ++ks) {
+                            const uint64_t ah = smem_desc_sw128(xaddr) + (uint64_t)(ks * 2);
+                            const uint64_t bh = smem_desc_sw128(bbase) + (uint64_t)(ks * 2);
+                            mma2_f16_ss(d, ah, bh, idesc, ks > 0);
+                            if (X3) {
+                                const uint64_t al = smem_desc_sw128(xaddr + 16384) + (uint64_t)(ks * 2);
+                                const uint64_t bl = smem_desc_sw128(bbase + 8192) + (uint64_t)(ks * 2);
+                                mma2_f16_ss(d, al, bh, idesc, 1);       // X_lo W_hi
+                                mma2_f16_ss(d, ah, bl, idesc, 1);       // X_hi W_lo
+                            }
                         }
+                        mma2_commit(bar_of(&bars->slot_empty[s]));
+                        mma2_commit(bar_of(&bars->d1_full[nc]));
                     }
-                    mma2_commit(smem_u32(&bars->slot_empty[s]));
-                    mma2_commit(smem_u32(&bars->d1_full[nc]));
-                    TRACE(0, i, 1 + nc);
+                    __syncwarp();
+                    if (lane == 0) TRACE(0, i, 1 + nc);
                 }
                 // ---- layer 2: D2 chunk nc = H1 W2'[128nc:128nc+128, :]^T, k in atoms of 64
                 for (int nc = 0; nc < C::NCH; ++nc) {
                     const uint32_t u = acc_u++, st = u & 1, ph = (u >> 1) & 1;
-                    mbar_wait(smem_u32(&bars->acc_empty[st]), ph ^ 1);
+                    mbar_wait(bar_of(&bars->acc_empty[st]), ph ^ 1);
                     tc_fence_after();
-                    TRACE(0, i, 3 + 6 * nc);
-                    const uint32_t d = tmem + (uint32_t)(C::ACC_BASE + st * kNC);
+                    if (lane == 0) TRACE(0, i, 3 + 6 * nc);
+                    const uint32_t d = tm + (uint32_t)(C::ACC_BASE + st * kNC);
                     for (int ka = 0; ka < C::KAT; ++ka) {
                         const uint32_t s = rs, sph = rph;
                         if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
-                        if (nc == 0 && (ka & 1) == 0) mbar_wait(smem_u32(&bars->h_ready[ka >> 1]), (uint32_t)i & 1);
-                        mbar_wait(smem_u32(&bars->slot_full[s]), sph);
+                        if (nc == 0 && (ka & 1) == 0) mbar_wait(bar_of(&bars->h_ready[ka >> 1]), (uint32_t)i & 1);
+                        mbar_wait(bar_of(&bars->slot_full[s]), sph);
                         tc_fence_after();
-                        TRACE(0, i, 4 + 6 * nc + ka);
-                        const uint32_t bbase = smem_u32(ring + (size_t)s * C::SLOT_BYTES);
+                        if (lane == 0) TRACE(0, i, 4 + 6 * nc + ka);
+                        const uint32_t bbase = ring_addr + s * (uint32_t)C::SLOT_BYTES;
+                        if (elect_one()) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            // H1 features 64ka + 16ks .. +16: group g = 2ka + ks/2, hi at column 32g + 8(ks%2), lo 16 further
-                            const uint32_t ah = tmem + (uint32_t)(32 * (2 * ka + (ks >> 1)) + 8 * (ks & 1));
-                            const uint64_t bh = smem_desc_sw128(bbase) + (uint64_t)(ks * 2);
-                            mma2_f16_ts(d, ah, bh, idesc, (ka | ks) != 0);
-                            if (X3) {
-                                const uint64_t bl = smem_desc_sw128(bbase + 8192) + (uint64_t)(ks * 2);
-                                mma2_f16_ts(d, ah + 16, bh, idesc, 1);      // H1_lo W_hi
-                                mma2_f16_ts(d, ah, bl, idesc, 1);           // H1_hi W_lo
+                            for (int ks = 0; ks < 4; ++ks) {
+                                // H1 features 64ka + 16ks .. +16: group g = 2ka + ks/2, hi at column 32g + 8(ks%2), lo 16 further
+                                const uint32_t ah = tm + (uint32_t)(32 * (2 * ka + (ks >> 1)) + 8 * (ks & 1));
+                                const uint64_t bh = smem_desc_sw128(bbase) + (uint64_t)(ks * 2);
+                                mma2_f16_ts(d, ah, bh, idesc, (ka | ks) != 0);
+                                if (X3) {
+                                    const uint64_t bl = smem_desc_sw128(bbase + 8192) + (uint64_t)(ks * 2);
+                                    mma2_f16_ts(d, ah + 16, bh, idesc, 1);      // H1_lo W_hi
+                                    mma2_f16_ts(d, ah, bl, idesc, 1);           // H1_hi W_lo
+                                }
                             }
+                            mma2_commit(bar_of(&bars->slot_empty[s]));
+                            if (ka == C::KAT - 1) mma2_commit(bar_of(&bars->acc_full[st]));
                         }
-                        mma2_commit(smem_u32(&bars->slot_empty[s]));
+                        __syncwarp();
                     }
-                    mma2_commit(smem_u32(&bars->acc_full[st]));
-                    TRACE(0, i, 8 + 6 * nc);
+                    if (lane == 0) TRACE(0, i, 8 + 6 * nc);
                 }
             }
         }
@@ -575,8 +619,17 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
         }
     } else if (warp < kGenWarps) {
         // =================================== weight generators =========================================
-        reg_dealloc<kGenRegs>();
+        if constexpr (kGenRegs < kLaunchRegs) reg_dealloc<kGenRegs>();
         const int gtid = threadIdx.x;                                   // 0..511
+        // producer-side waits: DES_PAIR_GEN_BACKOFF = sleep between polls (a generator that waits is ahead of its consumer:
+        // wake-up latency does not matter, the issue slots its polling would take from the epilogue warps do)
+        auto gen_wait = [](uint32_t bar, uint32_t parity) {
+#if defined(DES_PAIR_GEN_BACKOFF)
+            while (!mbar_try_wait(bar, parity)) asm volatile("nanosleep.u32 %0;" ::"r"((uint32_t)DES_PAIR_GEN_BACKOFF));
+#else
+            mbar_wait(bar, parity);
+#endif
+        };
         uint32_t rs = 0, rph = 0;                                       // ring cursor: slot index and phase
         const int r2 = gtid >> 3, c82 = gtid & 7;
         const int row_base = 64 * (int)rank;                            // this CTA's 64 rows of every 128-row chunk
@@ -595,9 +648,9 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
             //   layer-1 tile of chunk nc -> the half of the threads with (gtid >> 8) == (nc & 1);   W3' -> threads 0..A*H/4
             //   b1' -> warps 8..;   b2' -> warps 10..;   b3' -> warp 12.   Their theta comes from the resident copy.
             // ---- b1' (needed first)
-            mbar_wait(smem_u32(&bars->s1_empty[p]), ((mi >> 1) & 1) ^ 1);
+            gen_wait(smem_u32(&bars->s1_empty[p]), ((mi >> 1) & 1) ^ 1);
             {
-                const int k = gtid - 256;
+                const int k = gtid - kB1Off;
                 if (k >= 0 && k < H / 4) {
                     const float4 v1 = perturbed_quad((uint32_t)((L.off_b1 >> 2) + k), member, gen, kStreamNesEps, a.key,
                                                      a.neg2ln2_sigma2, lds128(th_base + th_b1_off + (uint32_t)k * 16));
@@ -610,9 +663,9 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
             for (int nc = 0; nc < C::NCH; ++nc) {
                 const uint32_t s = rs, sph = rph;
                 if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
-                mbar_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
+                gen_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
                 uint8_t *slot = ring + (size_t)s * C::SLOT_BYTES;
-                if ((gtid >> 8) == (nc & 1)) {   // 64 rows x 4 octets = 256 items
+                if ((gtid >> 8) == (kL1Alt ? (nc & 1) : 0)) {   // 64 rows x 4 octets = 256 items
                     const int lt = gtid & 255, r = lt >> 2, c8 = lt & 3;
                     const int n = nc * kNC + row_base + r;
                     const uint32_t trow = th_base + (uint32_t)((nc * 64 + r) * d0p * 4);
@@ -658,28 +711,34 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                     if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
                     const uint32_t stg = tq % kThStages, tph = (tq / kThStages) & 1;
                     ++tq;
-                    const int j0 = L.off_w2 + (nc * kNC + row_base + r2) * H + ka * 64 + c82 * 8;
-                    const uint4 x0 = philox4x32((uint32_t)(j0 >> 2), member, gen, kStreamNesEps, a.key);
-                    const uint4 x1 = philox4x32((uint32_t)(j0 >> 2) + 1, member, gen, kStreamNesEps, a.key);
-                    const BmParts pa = box_muller_parts(x0.x, x0.y, a.neg2ln2_sigma2);
-                    const BmParts pb = box_muller_parts(x0.z, x0.w, a.neg2ln2_sigma2);
-                    const BmParts pc = box_muller_parts(x1.x, x1.y, a.neg2ln2_sigma2);
-                    const BmParts pd = box_muller_parts(x1.z, x1.w, a.neg2ln2_sigma2);
+                    // octet o of this thread: tile row r2 + 32 o (kOct == 2: rows r2 and r2 + 32), k-octet c82
+                    BmParts pq[kOct][4];
+#pragma unroll
+                    for (int o = 0; o < kOct; ++o) {
+                        const int j0 = L.off_w2 + (nc * kNC + row_base + r2 + (64 / kOct) * o) * H + ka * 64 + c82 * 8;
+                        const uint4 x0 = philox4x32((uint32_t)(j0 >> 2), member, gen, kStreamNesEps, a.key);
+                        const uint4 x1 = philox4x32((uint32_t)(j0 >> 2) + 1, member, gen, kStreamNesEps, a.key);
+                        pq[o][0] = box_muller_parts(x0.x, x0.y, a.neg2ln2_sigma2);
+                        pq[o][1] = box_muller_parts(x0.z, x0.w, a.neg2ln2_sigma2);
+                        pq[o][2] = box_muller_parts(x1.x, x1.y, a.neg2ln2_sigma2);
+                        pq[o][3] = box_muller_parts(x1.z, x1.w, a.neg2ln2_sigma2);
+                    }
                     mbar_wait(smem_u32(&bars->th_full[stg]), tph);           // this slot's theta box has landed
-                    const uint32_t cell = smem_u32(th_stage + stg * kThetaStage) + (uint32_t)(r2 * 256 + c82 * 32);
-                    const float4 t0 = lds128(cell), t1 = lds128(cell + 16);
+                    float w[kOct][8];
+#pragma unroll
+                    for (int o = 0; o < kOct; ++o) {
+                        const uint32_t cell = smem_u32(th_stage + stg * kThetaStage) + (uint32_t)((r2 + (64 / kOct) * o) * 256 + c82 * 32);
+                        const float4 t0 = lds128(cell), t1 = lds128(cell + 16);
+                        w[o][0] = __fmaf_rn(pq[o][0].nr, pq[o][0].c, t0.x); w[o][1] = __fmaf_rn(pq[o][0].nr, pq[o][0].s, t0.y);
+                        w[o][2] = __fmaf_rn(pq[o][1].nr, pq[o][1].c, t0.z); w[o][3] = __fmaf_rn(pq[o][1].nr, pq[o][1].s, t0.w);
+                        w[o][4] = __fmaf_rn(pq[o][2].nr, pq[o][2].c, t1.x); w[o][5] = __fmaf_rn(pq[o][2].nr, pq[o][2].s, t1.y);
+                        w[o][6] = __fmaf_rn(pq[o][3].nr, pq[o][3].c, t1.z); w[o][7] = __fmaf_rn(pq[o][3].nr, pq[o][3].s, t1.w);
+                    }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&bars->th_empty[stg]));
-                    const float w[8] = {__fmaf_rn(pa.nr, pa.c, t0.x), __fmaf_rn(pa.nr, pa.s, t0.y),
-                                        __fmaf_rn(pb.nr, pb.c, t0.z), __fmaf_rn(pb.nr, pb.s, t0.w),
-                                        __fmaf_rn(pc.nr, pc.c, t1.x), __fmaf_rn(pc.nr, pc.s, t1.y),
-                                        __fmaf_rn(pd.nr, pd.c, t1.z), __fmaf_rn(pd.nr, pd.s, t1.w)};
-#ifdef DES_PAIR_GEN_BACKOFF
-                    mbar_wait_relaxed(smem_u32(&bars->slot_empty[s]), sph ^ 1);
-#else
-                    mbar_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
-#endif
-                    store_octet<X3>(ring + (size_t)s * C::SLOT_BYTES, r2, c82, w);
+                    gen_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
+#pragma unroll
+                    for (int o = 0; o < kOct; ++o) store_octet<X3>(ring + (size_t)s * C::SLOT_BYTES, r2 + (64 / kOct) * o, c82, w[o]);
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) arrive_leader(&bars->slot_full[s]);
@@ -687,20 +746,20 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                 }
                 if (nc == 0) {
                     // ---- b2', W3', b3': needed by the epilogue of layer 2, i.e. once the first output chunk has left the tensor pipe
-                    mbar_wait(smem_u32(&bars->s2_empty[p]), ((mi >> 1) & 1) ^ 1);
+                    gen_wait(smem_u32(&bars->s2_empty[p]), ((mi >> 1) & 1) ^ 1);
                     float *sm2 = small2 + p * s2_floats;
-                    if (gtid < L.A * H / 4)                                   // W3' [q][n] row-major: aligned quads
-                        reinterpret_cast<float4 *>(sm2 + H)[gtid] =
-                            perturbed_quad((uint32_t)((L.off_w3 >> 2) + gtid), member, gen, kStreamNesEps, a.key, a.neg2ln2_sigma2,
-                                           lds128(th_base + th_b1_off + (uint32_t)(2 * H * 4) + (uint32_t)gtid * 16));
+                    for (int k = gtid; k < L.A * H / 4; k += kGenThreads)     // W3' [q][n] row-major: aligned quads
+                        reinterpret_cast<float4 *>(sm2 + H)[k] =
+                            perturbed_quad((uint32_t)((L.off_w3 >> 2) + k), member, gen, kStreamNesEps, a.key, a.neg2ln2_sigma2,
+                                           lds128(th_base + th_b1_off + (uint32_t)(2 * H * 4) + (uint32_t)k * 16));
                     {
-                        const int k = gtid - 320;
+                        const int k = gtid - kB2Off;
                         if (k >= 0 && k < H / 4) {
                             const float4 v2 = perturbed_quad((uint32_t)((L.off_b2 >> 2) + k), member, gen, kStreamNesEps, a.key,
                                                              a.neg2ln2_sigma2, lds128(th_base + th_b1_off + (uint32_t)(H * 4) + (uint32_t)k * 16));
                             reinterpret_cast<float4 *>(sm2)[k] = make_float4(v2.x * bsc, v2.y * bsc, v2.z * bsc, v2.w * bsc);
                         }
-                        const int q = gtid - 384;
+                        const int q = gtid - kB3Off;
                         if (q >= 0 && q < L.A) {
                             const int jj = L.off_b3 + q;
                             const float4 z = noise_quad((uint32_t)(jj >> 2), member, gen, kStreamNesEps, a.key);
@@ -768,6 +827,10 @@ static int launch(Args &a, cudaStream_t st) {
                          16 + ((size_t)C::NCH * 64 * ((a.L.d0 + 3) & ~3) + 2 * H + (size_t)A4 * H + kMaxA + 128 * A4) * sizeof(float);
     int n_slots = (int)((227 * 1024 - fixed) / C::SLOT_BYTES);
     if (n_slots > 16) n_slots = 16;
+    if (const char *e = getenv("DES_PAIR_SLOTS")) {          // experiments: a shallower ring throttles the generators earlier
+        const int v = atoi(e);
+        if (v >= 4 && v < n_slots) n_slots = v;
+    }
     if (n_slots < 4) {
         set_error("des_nes_eval(tensor): no shared memory left for the weight ring (H=%d)", H);
         return DES_ERR_UNSUPPORTED;

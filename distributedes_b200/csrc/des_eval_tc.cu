@@ -139,6 +139,13 @@ __device__ __forceinline__ void put_octet(uint8_t *slot, int r, int c8, const ui
     if (X3) *reinterpret_cast<uint4 *>(slot + 8192 + off) = lo;
 }
 
+// one lane of a fully converged warp (see the MMA issuer)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 template <int REGS>
 __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 template <int REGS>
@@ -255,8 +262,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) eval_tc_kernel(TcArgs a) {
     const int64_t stride = PAIR ? gridDim.x / 2 : gridDim.x;
 
     if (warp == kMmaWarp) {
-        // =================================== MMA issuer (one thread) ===================================
-        if (lane == 0 && rank == 0) {
+        // =================================== MMA issuer ===================================
+        // The whole warp runs the loop converged and one elected lane issues, so every tcgen05 operand is warp-uniform
+        // (inside `if (lane == 0)` ptxas wrapped each tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop: ~160
+        // cycles per MMA, which made the issuing thread the bottleneck — round-2 trace of the pair kernel).
+        if (rank == 0) {
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+            auto slot_base_u = [&](int ts) { return tmem_u + (uint32_t)(ts * C::SLOT_COLS); };
             constexpr uint32_t idesc = idesc_f16(PAIR ? 256 : 128, kNC);
             uint32_t rs = 0, rph = 0;            // ring cursor: slot index and phase
             uint32_t acc_u[2] = {0, 0};          // accumulator-stage use counters per tile slot
@@ -274,8 +286,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) eval_tc_kernel(TcArgs a) {
                             const uint32_t u = acc_u[ts]++, st = u & 1, ph = (u >> 1) & 1;
                             mbar_wait(smem_u32(&bars->acc_empty[ts][st]), ph ^ 1);
                             tc_fence_after();
-                            const uint32_t d = slot_base(ts) + C::ACOLS + st * kNC;
+                            const uint32_t d = slot_base_u(ts) + C::ACOLS + st * kNC;
                             const uint32_t xaddr = smem_u32(xs + (size_t)(pass * NT + ts) * C::X_TILE_BYTES);
+                            if (elect_one()) {
 #pragma unroll
                             for (int ks = 0; ks < kK1 / 16; ++ks) {
                                 const uint64_t ah = smem_desc_sw128(xaddr) + (uint64_t)(ks * 2);
@@ -289,8 +302,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) eval_tc_kernel(TcArgs a) {
                                 }
                             }
                             commit(&bars->acc_full[ts][st]);
+                            }
+                            __syncwarp();
                         }
-                        commit(&bars->slot_empty[s]);
+                        if (elect_one()) commit(&bars->slot_empty[s]);
+                        __syncwarp();
                     }
                     // ---- layer 2: D2 chunk nc = H1 W2'[64nc:64nc+64, :]^T, k in atoms of 64
                     for (int nc = 0; nc < C::NCH; ++nc) {
@@ -299,7 +315,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) eval_tc_kernel(TcArgs a) {
                             const uint32_t u = acc_u[ts]++, st = u & 1, ph = (u >> 1) & 1;
                             mbar_wait(smem_u32(&bars->acc_empty[ts][st]), ph ^ 1);
                             st_[ts] = st;
-                            d_[ts] = slot_base(ts) + C::ACOLS + st * kNC;
+                            d_[ts] = slot_base_u(ts) + C::ACOLS + st * kNC;
                             if (nc == 0 && !kChunkedH) mbar_wait(smem_u32(&bars->h_ready[ts]), hv[ts] & 1);
                         }
                         tc_fence_after();
@@ -311,8 +327,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) eval_tc_kernel(TcArgs a) {
                             mbar_wait(smem_u32(&bars->slot_full[s]), sph);
                             tc_fence_after();
                             const uint32_t bbase = smem_u32(ring + (size_t)s * C::SLOT_BYTES);
+                            if (elect_one()) {
                             for (int ts = 0; ts < NT; ++ts) {
-                                const uint32_t ah = slot_base(ts) + ka * 32;
+                                const uint32_t ah = slot_base_u(ts) + ka * 32;
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks) {
                                     const uint64_t bh = smem_desc_sw128(bbase) + (uint64_t)(ks * 2);
@@ -326,14 +343,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) eval_tc_kernel(TcArgs a) {
                                 }
                             }
                             commit(&bars->slot_empty[s]);
+                            }
+                            __syncwarp();
                         }
+                        const bool issuer = elect_one();
                         for (int ts = 0; ts < NT; ++ts) {
-                            commit(&bars->acc_full[ts][st_[ts]]);
+                            if (issuer) commit(&bars->acc_full[ts][st_[ts]]);
                             if (nc == C::NCH - 1) {
-                                commit(&bars->h_free[ts]);
+                                if (issuer) commit(&bars->h_free[ts]);
                                 ++hv[ts];
                             }
                         }
+                        __syncwarp();
                     }
                 }
             }
