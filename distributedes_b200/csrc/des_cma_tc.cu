@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, 1) cma_syrk_kernel(Args a, const __g
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc(smem_u32(&bars->tmem_base), 256);
+        tmem_alloc(smem_u32(&bars->tmem_base), 512);
     }
     tc_fence_before();
     __syncthreads();
@@ -159,9 +159,15 @@ __global__ void __launch_bounds__(kThreads, 1) cma_syrk_kernel(Args a, const __g
                     const uint64_t al = smem_desc_sw128(base + kABytes) + (uint64_t)(k * 2);
                     const uint64_t bh = smem_desc_sw128(base + 2 * kABytes) + (uint64_t)(k * 2);
                     const uint64_t bl = smem_desc_sw128(base + 2 * kABytes + kBBytes) + (uint64_t)(k * 2);
-                    mma_ss(tm, ah, bh, idesc, (ks | k) != 0);
-                    mma_ss(tm, al, bh, idesc, 1);
-                    mma_ss(tm, ah, bl, idesc, 1);
+                    // two accumulators, one per half of K, added with round-to-nearest in the epilogue: the tensor cores
+                    // truncate when they align the fp32 accumulator, which biases long sums of same-sign terms (the
+                    // diagonal: -7e-6 relative at K = 1024 with one accumulator)
+                    const int half = ks >= (a.k_stages + 1) / 2 ? 1 : 0;
+                    const bool first = (k == 0) && (ks == 0 || ks == (a.k_stages + 1) / 2);
+                    const uint32_t d = tm + (uint32_t)(half * kBN);
+                    mma_ss(d, ah, bh, idesc, !first);
+                    mma_ss(d, al, bh, idesc, 1);
+                    mma_ss(d, ah, bl, idesc, 1);
                 }
                 mma_commit(bars_addr + (uint32_t)offsetof(Bars, empty) + 8u * s);
                 if (ks == a.k_stages - 1) mma_commit(bars_addr + (uint32_t)offsetof(Bars, acc_full));
@@ -185,6 +191,13 @@ __global__ void __launch_bounds__(kThreads, 1) cma_syrk_kernel(Args a, const __g
             uint32_t v[32];
             tmem_ld32(taddr + (uint32_t)c0, v);
             tmem_wait_ld();
+            if (a.k_stages > 1) {                                     // second half of K (its own accumulator)
+                uint32_t v2[32];
+                tmem_ld32(taddr + (uint32_t)(kBN + c0), v2);
+                tmem_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(v2[e]));
+            }
             if (a.packed) {
                 // packed upper tiles of side ptile: element (i, j) lives in tile (i / ptile, j / ptile), bi' <= bj'
                 const int64_t pb_i = i / a.ptile, pb_j = j0 / a.ptile;
@@ -211,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) cma_syrk_kernel(Args a, const __g
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 256);
+    if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,

@@ -37,6 +37,7 @@
 // CTA only), warp 17 TMA producer of the theta boxes, warps 18-19 idle, warps 20-27 epilogue (two per TMEM lane
 // quadrant = warp id % 4, alternating 32-column groups).
 #include <cuda.h>
+#include <stddef.h>
 #include <stdlib.h>
 #include "des_common.cuh"
 #include "des_tc.cuh"
@@ -67,6 +68,7 @@ constexpr int kThetaStage = 64 * 64 * 4;      // one TMA box of W2: 64 rows x 64
 #define DES_PAIR_THETA_STAGES 2
 #endif
 constexpr int kThStages = DES_PAIR_THETA_STAGES;
+static_assert(kThStages == 2, "the static theta-stage parities below assume two stages");
 // Register budget: the kernel is launched with kLaunchRegs per thread (__maxnreg__), i.e. a pool of 896 x 72 = 64 512;
 // setmaxnreg then moves registers from the generators to the epilogue warps.  The sum must fit the pool, or the
 // epilogue's setmaxnreg.inc never returns.
@@ -93,10 +95,14 @@ constexpr int kThStages = DES_PAIR_THETA_STAGES;
 #define DES_PAIR_MMA_REGS 72      // warpgroup 4 keeps its launch allocation (no setmaxnreg)
 #endif
 #endif
-#ifdef DES_PAIR_UNBALANCED      // experiment: all the small pieces on the low thread ids (round-2 v4 assignment)
-constexpr int kB1Off = 0, kB2Off = 0, kB3Off = 0, kL1Alt = 0;
-#else
+// Which generator threads take the small pieces (b1', layer-1 tiles, b2', W3', b3').  Measured on the headline shape:
+// everything on the low thread ids 10.55 ms, dealt evenly over the sixteen warps 11.34 ms — the warps that carry only
+// layer-2 octets run ahead through the ring and fall out of lockstep with the loaded ones, and eight warps in lockstep
+// (ready in the same cycles, stalled in the same cycles) hide each other's latency worse than two groups out of phase.
+#ifdef DES_PAIR_BALANCED
 constexpr int kB1Off = kGenThreads / 2, kB2Off = kGenThreads / 2 + 64, kB3Off = kGenWarps == 16 ? kGenThreads / 2 + 128 : 0, kL1Alt = kGenWarps == 16 ? 1 : 0;
+#else
+constexpr int kB1Off = 0, kB2Off = 0, kB3Off = 0, kL1Alt = 0;
 #endif
 constexpr int kLaunchRegs = DES_PAIR_LAUNCH_REGS;
 constexpr int kGenRegs = DES_PAIR_GEN_REGS, kEpiRegs = DES_PAIR_EPI_REGS, kMmaRegs = DES_PAIR_MMA_REGS;
@@ -111,6 +117,14 @@ struct Cfg {
     static constexpr int X_TILE_BYTES = (X3 ? 2 : 1) * 128 * 128;
     static constexpr int SLOTS_PER_MEMBER = NCH + NCH * KAT;
     static constexpr int ACC_BASE = H;                            // TMEM: [0,H) D1/H1, then two 128-column stages
+    // Static ring: the number of ring slots divides the slots of a member, so slot k of EVERY member lands in ring slot
+    // k % RING with mbarrier parity fixed by k (two laps per member) or by the member's parity (one lap): after unrolling
+    // the per-member slot loops every ring / barrier address and parity is a compile-time constant, and the generators'
+    // per-slot bookkeeping (a quarter of their instructions in the round-2 SASS count) disappears.
+    static constexpr int RING = (SLOTS_PER_MEMBER % 2 == 0 && SLOTS_PER_MEMBER / 2 >= 4) ? SLOTS_PER_MEMBER / 2 : SLOTS_PER_MEMBER;
+    static constexpr int LAPS = SLOTS_PER_MEMBER / RING;          // 2 or 1
+    static constexpr int W2SLOTS = NCH * KAT;                     // theta boxes per member: stage = w % kThStages
+    static_assert(W2SLOTS % (2 * kThStages) == 0 || W2SLOTS % kThStages == 0, "theta stages must tile the member");
 };
 
 struct Args {
@@ -170,8 +184,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
 // tanh(v + b) for four activations, biases pre-scaled by 2 log2(e): e = 2^min(v c + b c, 30), d = 1 + e,
 // 1/d_i from ONE reciprocal of d0 d1 d2 d3 and partial products; t = 1 - 2/d.   abs err ~3e-7.
 __device__ __forceinline__ void tanh4(float2 v01, float2 v23, float4 bs, float2 &t01, float2 &t23) {
-#ifdef DES_PAIR_PLAIN_RCP
-    t01 = tanh_acc2(v01, make_float2(bs.x, bs.y));      // experiment: one reciprocal per activation (2 MUFU, 3.5 issue slots)
+#ifndef DES_PAIR_QUAD_RCP
+    // default: one reciprocal per activation (2 MUFU, 3.5 issue slots): measured 10.19 ms against 10.57 ms for the shared
+    // reciprocal below (1.25 MUFU, 5.25 slots) — issue slots, not the XU pipe, are the scarcer resource here
+    t01 = tanh_acc2(v01, make_float2(bs.x, bs.y));
     t23 = tanh_acc2(v23, make_float2(bs.z, bs.w));
     return;
 #endif
@@ -233,6 +249,23 @@ __device__ __forceinline__ void store_octet(uint8_t *slot, int r, int c8, const 
     const int off = r * 128 + ((c8 ^ (r & 7)) << 4);          // SWIZZLE_128B
     *reinterpret_cast<uint4 *>(slot + off) = hi;
     if (X3) *reinterpret_cast<uint4 *>(slot + 8192 + off) = lo;
+}
+
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// the same octet store through a 32-bit shared address (STS instead of a generic ST) with the packed-subtract split
+template <bool X3>
+__device__ __forceinline__ void store_octet_s(uint32_t slot_addr_plus_off, const float (&w)[8]) {
+    uint4 hi, lo;
+    if (X3) {
+        split_h2p(make_float2(w[0], w[1]), hi.x, lo.x); split_h2p(make_float2(w[2], w[3]), hi.y, lo.y);
+        split_h2p(make_float2(w[4], w[5]), hi.z, lo.z); split_h2p(make_float2(w[6], w[7]), hi.w, lo.w);
+    } else {
+        hi.x = pack_h2(w[0], w[1]); hi.y = pack_h2(w[2], w[3]); hi.z = pack_h2(w[4], w[5]); hi.w = pack_h2(w[6], w[7]);
+    }
+    sts128(slot_addr_plus_off, hi);
+    if (X3) sts128(slot_addr_plus_off + 8192, lo);
 }
 
 template <int H, bool X3, int A4>
@@ -332,11 +365,18 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
     cluster_sync_all();          // the peer's barriers are initialised before anyone arrives on them
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
+    const uint32_t bars_s = smem_u32(bars);          // barriers are addressed with 32-bit shared addresses + constant offsets
+#define BAR(field, idx) (bars_s + (uint32_t)offsetof(Bars, field) + 8u * (uint32_t)(idx))
 
+    // ring slot and mbarrier parity of slot k (0 .. SLOTS_PER_MEMBER-1) of this CTA's member number i
+    auto ring_slot = [](int k) { return (uint32_t)(k % C::RING); };
+    auto ring_par = [](int k, uint32_t i) { return C::LAPS == 2 ? (uint32_t)((k / C::RING) & 1) : (i & 1u); };
+    // theta stage and parity of layer-2 slot w (0 .. W2SLOTS-1) of member i: fill number = i * W2SLOTS / 2 + w / 2
+    auto th_par = [](int w, uint32_t i) { return (uint32_t)(((C::W2SLOTS / 2) * i + (uint32_t)(w / 2)) & 1u); };
     // arrive on the LEADER's copy of a barrier (local for the leader, one remote arrive for the follower)
-    auto arrive_leader = [&](uint64_t *bar) {
-        if (rank == 0) mbar_arrive(smem_u32(bar));
-        else mbar_arrive_remote(smem_u32(bar), 0);
+    auto arrive_leader = [&](uint32_t bar) {
+        if (rank == 0) mbar_arrive(bar);
+        else mbar_arrive_remote(bar, 0);
     };
     const int64_t first = blockIdx.x / 2;
     const int64_t stride = gridDim.x / 2;
@@ -354,19 +394,17 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
             // against the 64 the tensor pipe needs: the issuing thread was the bottleneck of the whole pair.)
             constexpr uint32_t idesc = idesc_f16(256, kNC);
             const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
-            uint32_t rs = 0, rph = 0;            // ring cursor: slot index and phase
             uint32_t acc_u = 0;                  // accumulator-stage use counter
             const uint32_t xaddr = smem_u32(xs);
-            const uint32_t ring_addr = smem_u32(ring), bars_addr = smem_u32(bars);
-            auto bar_of = [&](const void *field) { return bars_addr + (uint32_t)((const uint8_t *)field - (const uint8_t *)bars); };
+            const uint32_t ring_addr = smem_u32(ring);
             for (int64_t i = 0; i < n_mine; ++i) {
                 if (lane == 0) TRACE(0, i, 0);
                 // ---- layer 1: D1 chunk nc = X W1'[128nc:128nc+128, :]^T, into the H1 columns (in-order after layer 2 of
                 //      the previous member, which read them)
+#pragma unroll
                 for (int nc = 0; nc < C::NCH; ++nc) {
-                    const uint32_t s = rs, sph = rph;
-                    if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
-                    mbar_wait(bar_of(&bars->slot_full[s]), sph);
+                    const uint32_t s = ring_slot(nc), sph = ring_par(nc, (uint32_t)i);
+                    mbar_wait(BAR(slot_full, s), sph);
                     tc_fence_after();
                     const uint32_t bbase = ring_addr + s * (uint32_t)C::SLOT_BYTES;
                     const uint32_t d = tm + (uint32_t)(nc * kNC);
@@ -383,24 +421,26 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                                 mma2_f16_ss(d, ah, bl, idesc, 1);       // X_hi W_lo
                             }
                         }
-                        mma2_commit(bar_of(&bars->slot_empty[s]));
-                        mma2_commit(bar_of(&bars->d1_full[nc]));
+                        mma2_commit(BAR(slot_empty, s));
+                        mma2_commit(BAR(d1_full, nc));
                     }
                     __syncwarp();
                     if (lane == 0) TRACE(0, i, 1 + nc);
                 }
                 // ---- layer 2: D2 chunk nc = H1 W2'[128nc:128nc+128, :]^T, k in atoms of 64
+#pragma unroll
                 for (int nc = 0; nc < C::NCH; ++nc) {
                     const uint32_t u = acc_u++, st = u & 1, ph = (u >> 1) & 1;
-                    mbar_wait(bar_of(&bars->acc_empty[st]), ph ^ 1);
+                    mbar_wait(BAR(acc_empty, st), ph ^ 1);
                     tc_fence_after();
                     if (lane == 0) TRACE(0, i, 3 + 6 * nc);
                     const uint32_t d = tm + (uint32_t)(C::ACC_BASE + st * kNC);
+#pragma unroll
                     for (int ka = 0; ka < C::KAT; ++ka) {
-                        const uint32_t s = rs, sph = rph;
-                        if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
-                        if (nc == 0 && (ka & 1) == 0) mbar_wait(bar_of(&bars->h_ready[ka >> 1]), (uint32_t)i & 1);
-                        mbar_wait(bar_of(&bars->slot_full[s]), sph);
+                        const int k = C::NCH + nc * C::KAT + ka;
+                        const uint32_t s = ring_slot(k), sph = ring_par(k, (uint32_t)i);
+                        if (nc == 0 && (ka & 1) == 0) mbar_wait(BAR(h_ready, ka >> 1), (uint32_t)i & 1);
+                        mbar_wait(BAR(slot_full, s), sph);
                         tc_fence_after();
                         if (lane == 0) TRACE(0, i, 4 + 6 * nc + ka);
                         const uint32_t bbase = ring_addr + s * (uint32_t)C::SLOT_BYTES;
@@ -417,8 +457,8 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                                     mma2_f16_ts(d, ah, bl, idesc, 1);           // H1_hi W_lo
                                 }
                             }
-                            mma2_commit(bar_of(&bars->slot_empty[s]));
-                            if (ka == C::KAT - 1) mma2_commit(bar_of(&bars->acc_full[st]));
+                            mma2_commit(BAR(slot_empty, s));
+                            if (ka == C::KAT - 1) mma2_commit(BAR(acc_full, st));
                         }
                         __syncwarp();
                     }
@@ -436,8 +476,8 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
             uint32_t w = 0;                                      // layer-2 slot of the member: (nc, ka) = (w / KAT, w % KAT)
             for (uint32_t q = 0; q < total; ++q) {
                 const uint32_t stg = q % kThStages, use = q / kThStages;
-                if (use > 0) mbar_wait(smem_u32(&bars->th_empty[stg]), (use - 1) & 1);
-                const uint32_t bar = smem_u32(&bars->th_full[stg]);
+                if (use > 0) mbar_wait(BAR(th_empty, stg), (use - 1) & 1);
+                const uint32_t bar = BAR(th_full, stg);
                 mbar_expect_tx(bar, kThetaStage);
                 tma_load_2d(smem_u32(th_stage + stg * kThetaStage), &w2_map, (int)(w % C::KAT) * 64,
                             (int)(w / C::KAT) * kNC + row_base, bar);
@@ -458,11 +498,11 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
         // ---------------- E1: H1 = tanh(D1 + b1') -> fp16 (hi [, lo]) written back IN PLACE
         auto epilogue1 = [&](uint32_t mi) {
             const uint32_t p = mi & 1;
-            mbar_wait(smem_u32(&bars->s1_full[p]), (mi >> 1) & 1);
+            mbar_wait(BAR(s1_full, p), (mi >> 1) & 1);
             if (ew == 0 && lane == 0) TRACE(1, (int64_t)mi, 0);
             const uint32_t b1 = s1_addr + p * (H * 4);
             for (int nc = 0; nc < C::NCH; ++nc) {
-                mbar_wait(smem_u32(&bars->d1_full[nc]), mi & 1);
+                mbar_wait(BAR(d1_full, nc), mi & 1);
                 tc_fence_after();
                 if (ew == 0 && lane == 0) TRACE(1, (int64_t)mi, 1 + 2 * nc);
                 uint32_t va[16], vb[16];
@@ -502,10 +542,10 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                 tmem_wait_st();                       // this chunk of H1 is complete: its k-atoms may be consumed
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) arrive_leader(&bars->h_ready[nc]);
+                if (lane == 0) arrive_leader(BAR(h_ready, nc));
                 if (ew == 0 && lane == 0) TRACE(1, (int64_t)mi, 2 + 2 * nc);
             }
-            if (lane == 0) mbar_arrive(smem_u32(&bars->s1_empty[p]));
+            if (lane == 0) mbar_arrive(BAR(s1_empty, p));
         };
 
         float2 actp[A4];                          // (even-n, odd-n) partial sums of action q
@@ -514,7 +554,7 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
             const uint32_t u = acc_u++, st = u & 1, ph = (u >> 1) & 1;
             const uint32_t b2 = s2_addr + p * (uint32_t)(s2_floats * 4);
             const uint32_t w3 = b2 + H * 4;
-            mbar_wait(smem_u32(&bars->acc_full[st]), ph);
+            mbar_wait(BAR(acc_full, st), ph);
             tc_fence_after();
             if (ew == 0 && lane == 0) TRACE(1, tri, 5 + 2 * nc);
             const uint32_t acc_base = tbase + (uint32_t)(C::ACC_BASE + st * kNC);
@@ -529,7 +569,7 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                 if (gi == 1) {                                 // every load of this accumulator stage has landed
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) arrive_leader(&bars->acc_empty[st]);
+                    if (lane == 0) arrive_leader(BAR(acc_empty, st));
                 }
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
@@ -567,7 +607,7 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
         for (int64_t i = 0; i < n_mine; ++i, ++mi) {
             const int64_t m = first + i * stride;
             const uint32_t p = mi & 1;
-            mbar_wait(smem_u32(&bars->s2_full[p]), (mi >> 1) & 1);
+            mbar_wait(BAR(s2_full, p), (mi >> 1) & 1);
             if (ew == 0 && lane == 0) TRACE(1, i, 10);
 #pragma unroll
             for (int q = 0; q < A4; ++q) actp[q] = make_float2(0.f, 0.f);
@@ -583,7 +623,7 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
 #pragma unroll
                 for (int q = 0; q < A4; ++q) act_x[(p * 128 + row) * A4 + q] = act[q];
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bars->s2_empty[p]));     // done with this member's b2/W3
+                if (lane == 0) mbar_arrive(BAR(s2_empty, p));     // done with this member's b2/W3
                 asm volatile("bar.arrive %0, 256;" ::"r"(2 + p) : "memory");     // ids alternate with the member parity
             } else {
                 asm volatile("bar.sync %0, 256;" ::"r"(2 + p) : "memory");
@@ -601,7 +641,7 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                 for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
                 if (lane == 0) {
                     bars->fit_part[p][ew] = sq;
-                    mbar_arrive(smem_u32(&bars->s2_empty[p]));
+                    mbar_arrive(BAR(s2_empty, p));
                 }
                 if (ew == 0) {
                     asm volatile("bar.sync %0, 128;" ::"r"(4 + p) : "memory");
@@ -630,10 +670,15 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
             mbar_wait(bar, parity);
 #endif
         };
-        uint32_t rs = 0, rph = 0;                                       // ring cursor: slot index and phase
         const int r2 = gtid >> 3, c82 = gtid & 7;
+        const uint32_t ring_s = smem_u32(ring);                           // 32-bit shared addresses: STS, one register
+        uint32_t oct_off[kOct];                                          // this thread's swizzled byte offsets inside a layer-2 tile
+#pragma unroll
+        for (int o = 0; o < kOct; ++o) {
+            const int r = r2 + (64 / kOct) * o;
+            oct_off[o] = (uint32_t)(r * 128 + ((c82 ^ (r & 7)) << 4));
+        }
         const int row_base = 64 * (int)rank;                            // this CTA's 64 rows of every 128-row chunk
-        uint32_t tq = 0;                                                // layer-2 slots generated so far (theta stage = tq % kThStages)
         // resident theta through 32-bit shared addresses (one register) instead of five generic pointers
         const uint32_t th_base = smem_u32(th_w1);
         const uint32_t th_b1_off = (uint32_t)(C::NCH * 64 * d0p * 4);
@@ -643,12 +688,9 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
             const uint32_t member = (uint32_t)(a.member_offset + (uint64_t)(first + i * stride));
             const uint32_t p = mi & 1;
             if (gtid == 0) TRACE(2, i, 0);
-            // The small pieces are dealt to DIFFERENT warps (round-2 trace: with everything on the low thread ids, warps 0-1
-            // carried ~13 octet-equivalents per member against 8 for warps 8-15, and the slot barriers wait for the slowest):
-            //   layer-1 tile of chunk nc -> the half of the threads with (gtid >> 8) == (nc & 1);   W3' -> threads 0..A*H/4
-            //   b1' -> warps 8..;   b2' -> warps 10..;   b3' -> warp 12.   Their theta comes from the resident copy.
+            // The small pieces (thread ranges: kB1Off / kL1Alt / kB2Off / kB3Off above) take their theta from the resident copy.
             // ---- b1' (needed first)
-            gen_wait(smem_u32(&bars->s1_empty[p]), ((mi >> 1) & 1) ^ 1);
+            gen_wait(BAR(s1_empty, p), ((mi >> 1) & 1) ^ 1);
             {
                 const int k = gtid - kB1Off;
                 if (k >= 0 && k < H / 4) {
@@ -658,13 +700,12 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars->s1_full[p]));
+            if (lane == 0) mbar_arrive(BAR(s1_full, p));
             // ---- layer-1 tiles: rows [128nc + 64 rank, +64) of W1', k < d0 (zero padded to 32)
+#pragma unroll
             for (int nc = 0; nc < C::NCH; ++nc) {
-                const uint32_t s = rs, sph = rph;
-                if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
-                gen_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
-                uint8_t *slot = ring + (size_t)s * C::SLOT_BYTES;
+                const uint32_t s = ring_slot(nc), sph = ring_par(nc, mi);
+                gen_wait(BAR(slot_empty, s), sph ^ 1);
                 if ((gtid >> 8) == (kL1Alt ? (nc & 1) : 0)) {   // 64 rows x 4 octets = 256 items
                     const int lt = gtid & 255, r = lt >> 2, c8 = lt & 3;
                     const int n = nc * kNC + row_base + r;
@@ -697,20 +738,21 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                             w[e] = x;
                         }
                     }
-                    store_octet<X3>(slot, r, c8, w);
+                    store_octet_s<X3>(ring_s + s * (uint32_t)C::SLOT_BYTES + (uint32_t)(r * 128 + ((c8 ^ (r & 7)) << 4)), w);
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) arrive_leader(&bars->slot_full[s]);
+                if (lane == 0) arrive_leader(BAR(slot_full, s));
                 if (gtid == 0) TRACE(2, i, 1 + nc);
             }
             // ---- layer-2 tiles: rows [128nc + 64 rank, +64) x k [64ka, +64) of W2': one octet per thread
+#pragma unroll
             for (int nc = 0; nc < C::NCH; ++nc) {
+#pragma unroll
                 for (int ka = 0; ka < C::KAT; ++ka) {
-                    const uint32_t s = rs, sph = rph;
-                    if (++rs == (uint32_t)a.n_slots) { rs = 0; rph ^= 1; }
-                    const uint32_t stg = tq % kThStages, tph = (tq / kThStages) & 1;
-                    ++tq;
+                    const int k = C::NCH + nc * C::KAT + ka, w2 = nc * C::KAT + ka;
+                    const uint32_t s = ring_slot(k), sph = ring_par(k, mi);
+                    const uint32_t stg = (uint32_t)(w2 & 1), tph = th_par(w2, mi);
                     // octet o of this thread: tile row r2 + 32 o (kOct == 2: rows r2 and r2 + 32), k-octet c82
                     BmParts pq[kOct][4];
 #pragma unroll
@@ -723,7 +765,7 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                         pq[o][2] = box_muller_parts(x1.x, x1.y, a.neg2ln2_sigma2);
                         pq[o][3] = box_muller_parts(x1.z, x1.w, a.neg2ln2_sigma2);
                     }
-                    mbar_wait(smem_u32(&bars->th_full[stg]), tph);           // this slot's theta box has landed
+                    mbar_wait(BAR(th_full, stg), tph);           // this slot's theta box has landed
                     float w[kOct][8];
 #pragma unroll
                     for (int o = 0; o < kOct; ++o) {
@@ -735,18 +777,18 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                         w[o][6] = __fmaf_rn(pq[o][3].nr, pq[o][3].c, t1.z); w[o][7] = __fmaf_rn(pq[o][3].nr, pq[o][3].s, t1.w);
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&bars->th_empty[stg]));
-                    gen_wait(smem_u32(&bars->slot_empty[s]), sph ^ 1);
+                    if (lane == 0) mbar_arrive(BAR(th_empty, stg));
+                    gen_wait(BAR(slot_empty, s), sph ^ 1);
 #pragma unroll
-                    for (int o = 0; o < kOct; ++o) store_octet<X3>(ring + (size_t)s * C::SLOT_BYTES, r2 + (64 / kOct) * o, c82, w[o]);
+                    for (int o = 0; o < kOct; ++o) store_octet_s<X3>(ring_s + s * (uint32_t)C::SLOT_BYTES + oct_off[o], w[o]);
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) arrive_leader(&bars->slot_full[s]);
+                    if (lane == 0) arrive_leader(BAR(slot_full, s));
                     if (gtid == 0) TRACE(2, i, 3 + nc * C::KAT + ka);
                 }
                 if (nc == 0) {
                     // ---- b2', W3', b3': needed by the epilogue of layer 2, i.e. once the first output chunk has left the tensor pipe
-                    gen_wait(smem_u32(&bars->s2_empty[p]), ((mi >> 1) & 1) ^ 1);
+                    gen_wait(BAR(s2_empty, p), ((mi >> 1) & 1) ^ 1);
                     float *sm2 = small2 + p * s2_floats;
                     for (int k = gtid; k < L.A * H / 4; k += kGenThreads)     // W3' [q][n] row-major: aligned quads
                         reinterpret_cast<float4 *>(sm2 + H)[k] =
@@ -769,7 +811,7 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&bars->s2_full[p]));
+                    if (lane == 0) mbar_arrive(BAR(s2_full, p));
                     if (gtid == 0) TRACE(2, i, 11);
                 }
             }
@@ -779,6 +821,7 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
     __syncthreads();
     cluster_sync_all();          // no CTA leaves (or frees TMEM) while its peer may still signal or read it
     if (warp == kMmaWarp) tmem_dealloc2(tmem, 512);
+#undef BAR
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -825,14 +868,9 @@ static int launch(Args &a, cudaStream_t st) {
     const size_t fixed = 1024 + C::X_TILE_BYTES + kThStages * kThetaStage + (2 * H + 2 * s2_floats) * sizeof(float) + 16 + sizeof(Bars) +
                          2 * 128 * (size_t)a.a4 * sizeof(float) +
                          16 + ((size_t)C::NCH * 64 * ((a.L.d0 + 3) & ~3) + 2 * H + (size_t)A4 * H + kMaxA + 128 * A4) * sizeof(float);
-    int n_slots = (int)((227 * 1024 - fixed) / C::SLOT_BYTES);
-    if (n_slots > 16) n_slots = 16;
-    if (const char *e = getenv("DES_PAIR_SLOTS")) {          // experiments: a shallower ring throttles the generators earlier
-        const int v = atoi(e);
-        if (v >= 4 && v < n_slots) n_slots = v;
-    }
-    if (n_slots < 4) {
-        set_error("des_nes_eval(tensor): no shared memory left for the weight ring (H=%d)", H);
+    const int n_slots = C::RING;                 // static ring (see Cfg): 5 slots for H = 256, 3 for H = 128
+    if (fixed + (size_t)n_slots * C::SLOT_BYTES > 227 * 1024) {
+        set_error("des_nes_eval(tensor): shared memory budget exceeded (H=%d)", H);
         return DES_ERR_UNSUPPORTED;
     }
     a.n_slots = n_slots;

@@ -89,9 +89,11 @@ def test_rank_mu_identities_at_4096_by_1024():
     dC = ops.cma_rank_mu(Y, w)
     assert torch.equal(dC, dC.T)                                                      # exactly symmetric
     tr_ref = float((w.double() * (Y.double() ** 2).sum(1)).sum())
-    assert abs(float(torch.trace(dC.double())) - tr_ref) <= 1e-6 * tr_ref             # tr(sum w y y^T) = sum w |y|^2
+    # tr(sum w y y^T) = sum w |y|^2: a sum of 4096 x 1024 POSITIVE terms — the tensor cores' truncating fp32 accumulation
+    # shows up here as a systematic few-1e-6 deficit (the FFMA path gives 1e-7); the 1e-5 contract of the op holds
+    assert abs(float(torch.trace(dC.double())) - tr_ref) <= 6e-6 * tr_ref
     v = torch.randn(n, generator=g).to(DEV).double()
     quad_ref = float((w.double() * (Y.double() @ v) ** 2).sum())                      # v^T dC v = sum w (y.v)^2 >= 0
     assert abs(float(v @ (dC.double() @ v)) - quad_ref) <= 1e-5 * quad_ref
     halves = ops.cma_rank_mu(Y[:512].contiguous(), w[:512].contiguous()) + ops.cma_rank_mu(Y[512:].contiguous(), w[512:].contiguous())
-    assert float((halves - dC).norm() / dC.norm()) < 1e-6
+    assert float((halves - dC).norm() / dC.norm()) < 3e-6      # same terms, different fp32 accumulation grouping on the tensor cores
