@@ -95,14 +95,18 @@ static_assert(kThStages == 2, "the static theta-stage parities below assume two 
 #define DES_PAIR_MMA_REGS 72      // warpgroup 4 keeps its launch allocation (no setmaxnreg)
 #endif
 #endif
-// Which generator threads take the small pieces (b1', layer-1 tiles, b2', W3', b3').  Measured on the headline shape:
-// everything on the low thread ids 10.55 ms, dealt evenly over the sixteen warps 11.34 ms — the warps that carry only
-// layer-2 octets run ahead through the ring and fall out of lockstep with the loaded ones, and eight warps in lockstep
-// (ready in the same cycles, stalled in the same cycles) hide each other's latency worse than two groups out of phase.
-#ifdef DES_PAIR_BALANCED
+// Which generator threads take the small pieces (b1', layer-1 tiles, b2', W3', b3').  Measured on the headline shape
+// (static-ring build): bias vectors on the upper warps, tiles and W3' on the lower ones 8.84 ms (default); everything on the
+// low thread ids 8.99 ms; layer-1 tiles alternating between the halves as well 8.96 ms.  (Before the static ring the fully
+// even deal was the SLOWEST, 11.3 vs 10.5 ms: warps that carry only layer-2 octets run ahead through the ring and fall out
+// of lockstep with the loaded ones, and warps in lockstep — ready in the same cycles, stalled in the same cycles — hide
+// each other's latency worse than two groups out of phase.)
+#if defined(DES_PAIR_BALANCED)
 constexpr int kB1Off = kGenThreads / 2, kB2Off = kGenThreads / 2 + 64, kB3Off = kGenWarps == 16 ? kGenThreads / 2 + 128 : 0, kL1Alt = kGenWarps == 16 ? 1 : 0;
-#else
+#elif defined(DES_PAIR_LOW_IDS)
 constexpr int kB1Off = 0, kB2Off = 0, kB3Off = 0, kL1Alt = 0;
+#else
+constexpr int kB1Off = kGenThreads / 2, kB2Off = kGenThreads / 2 + 64, kB3Off = kGenWarps == 16 ? kGenThreads / 2 + 128 : 0, kL1Alt = 0;
 #endif
 constexpr int kLaunchRegs = DES_PAIR_LAUNCH_REGS;
 constexpr int kGenRegs = DES_PAIR_GEN_REGS, kEpiRegs = DES_PAIR_EPI_REGS, kMmaRegs = DES_PAIR_MMA_REGS;
