@@ -115,20 +115,30 @@ static_assert(kGenWarps * 32 * kGenRegs + kEpiWarps * 32 * kEpiRegs + 4 * 32 * k
 
 template <int H, bool X3>
 struct Cfg {
-    static constexpr int NCH = H / kNC;                          // output-feature chunks per layer
-    static constexpr int KAT = H / 64;                           // 64-wide k atoms of layer 2
+    // Hidden widths below 256 run MB = 256 / H members SIDE BY SIDE as one "super-member" of effective width HH = 256:
+    // effective hidden unit F = j * H + f is unit f of member j.  Layer 1 is then one GEMM for all MB members (X is shared),
+    // layer 2 is block diagonal (member j's H1 block against member j's W2'), and every per-member overhead of the
+    // pipeline (barrier round trips, epilogue phases, small arrays) is paid once per MB members — the pop-4096 / 2x64
+    // configuration (BASELINE configs[1]) was latency-bound at one member per CTA.
+    static constexpr int HH = 256;
+    static constexpr int MB = HH / H;                             // members per super-member: 1, 2 or 4
+    static constexpr int NCH = HH / kNC;                          // output-feature chunks per layer (2)
+    static constexpr int KATC = H == 256 ? 4 : (H == 128 ? 2 : 1);   // layer-2 slots per chunk (only the diagonal blocks)
+    static constexpr int MC = MB == 4 ? 2 : 1;                    // members finished by one chunk of layer 2
     static constexpr int SLOT_BYTES = (X3 ? 2 : 1) * 64 * 128;   // this CTA's B tile: 64 rows x 128 B (hi [+ lo])
     static constexpr int X_TILE_BYTES = (X3 ? 2 : 1) * 128 * 128;
-    static constexpr int SLOTS_PER_MEMBER = NCH + NCH * KAT;
-    static constexpr int ACC_BASE = H;                            // TMEM: [0,H) D1/H1, then two 128-column stages
+    static constexpr int SLOTS_PER_MEMBER = NCH + NCH * KATC;     // per super-member: 10, 6 or 4
+    static constexpr int ACC_BASE = HH;                           // TMEM: [0,256) D1/H1, then two 128-column stages
     // Static ring: the number of ring slots divides the slots of a member, so slot k of EVERY member lands in ring slot
     // k % RING with mbarrier parity fixed by k (two laps per member) or by the member's parity (one lap): after unrolling
     // the per-member slot loops every ring / barrier address and parity is a compile-time constant, and the generators'
     // per-slot bookkeeping (a quarter of their instructions in the round-2 SASS count) disappears.
     static constexpr int RING = (SLOTS_PER_MEMBER % 2 == 0 && SLOTS_PER_MEMBER / 2 >= 4) ? SLOTS_PER_MEMBER / 2 : SLOTS_PER_MEMBER;
     static constexpr int LAPS = SLOTS_PER_MEMBER / RING;          // 2 or 1
-    static constexpr int W2SLOTS = NCH * KAT;                     // theta boxes per member: stage = w % kThStages
-    static_assert(W2SLOTS % (2 * kThStages) == 0 || W2SLOTS % kThStages == 0, "theta stages must tile the member");
+    static constexpr int W2SLOTS = NCH * KATC;                    // theta boxes per super-member: stage = w % kThStages
+    static_assert(W2SLOTS % 2 == 0, "theta stages must tile the member");
+    static constexpr int TH_ROWS = H == 64 ? 32 : 64;             // rows of fc2.weight in one theta box
+    static constexpr int TH_BYTES = TH_ROWS * 64 * 4;
 };
 
 struct Args {
@@ -151,7 +161,7 @@ struct Bars {
     uint64_t s1_full[2], s1_empty[2], s2_full[2], s2_empty[2];
     uint64_t d1_full[2], h_ready[2], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
-    float fit_part[2][4];
+    float fit_part[2][4][2];
 };
 
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
@@ -281,17 +291,18 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
     uint8_t *xs = smem;                                                    // X tile (hi [, lo])
     uint8_t *ring = xs + C::X_TILE_BYTES;                                  // n_slots * SLOT_BYTES
     uint8_t *th_stage = ring + (size_t)a.n_slots * C::SLOT_BYTES;          // kThStages x 16 KB TMA destinations
-    float *small1 = reinterpret_cast<float *>(th_stage + kThStages * kThetaStage); // [2][H]: b1' * 2log2e
-    const int s2_floats = H + A4 * H + kMaxA;                            // b2' * 2log2e | W3' [a4][H] | b3'[8]
-    float *small2 = small1 + 2 * H;                                        // [2][s2_floats]
+    constexpr int HH = C::HH, MB = C::MB, MC = C::MC;
+    float *small1 = reinterpret_cast<float *>(th_stage + kThStages * kThetaStage); // [2][HH]: b1' * 2log2e (effective units)
+    constexpr int s2_floats = HH + A4 * HH + MB * kMaxA;                   // b2' * 2log2e | W3' [a4][HH] | b3' [MB][8]
+    float *small2 = small1 + 2 * HH;                                       // [2][s2_floats]
     Bars *bars = reinterpret_cast<Bars *>((reinterpret_cast<uintptr_t>(small2 + 2 * s2_floats) + 15) & ~(uintptr_t)15);
-    // action partial sums handed from the odd-group warp to the even-group warp of a quadrant: [2][128 rows][a4]
+    // action partial sums handed from the odd-group warp to the even-group warp of a quadrant: [2][128 rows][MC][a4]
     float *act_x = reinterpret_cast<float *>(bars + 1);
     // member-independent theta the generators add their noise to, resident for the whole kernel (round-2 trace: the
     // __ldg latency of these small pieces sat on the slowest generator warps' critical path every member):
     //   W1 rows of this CTA [NCH*64][d0p] | b1 [H] | b2 [H] | W3 [A][H] | b3 [A -> 4-padded]
     const int d0p = (a.L.d0 + 3) & ~3;
-    float *th_w1 = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(act_x + 2 * 128 * A4) + 15) & ~(uintptr_t)15);
+    float *th_w1 = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(act_x + 2 * 128 * MC * A4) + 15) & ~(uintptr_t)15);
     float *th_b1 = th_w1 + C::NCH * 64 * d0p;
     float *th_b2 = th_b1 + H;
     float *th_w3 = th_b2 + H;
@@ -349,8 +360,8 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
     // unused action rows of W3' stay zero (finite) in both buffers
     for (int i = threadIdx.x; i < 2 * s2_floats; i += blockDim.x) small2[i] = 0.f;
     for (int i = threadIdx.x; i < C::NCH * 64 * d0p; i += blockDim.x) {
-        const int lr = i / d0p, k = i - lr * d0p;                       // local row = nc*64 + r  ->  W1 row nc*128 + 64 rank + r
-        const int n = (lr >> 6) * kNC + 64 * (int)rank + (lr & 63);
+        const int lr = i / d0p, k = i - lr * d0p;                       // local row = nc*64 + r -> effective unit nc*128 + 64 rank + r
+        const int n = ((lr >> 6) * kNC + 64 * (int)rank + (lr & 63)) % H;   // -> W1 row of whichever member owns that unit
         th_w1[i] = k < L.d0 ? __ldg(a.theta + L.off_w1 + n * L.d0 + k) : 0.f;
     }
     for (int i = threadIdx.x; i < H; i += blockDim.x) {
@@ -384,7 +395,8 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
     };
     const int64_t first = blockIdx.x / 2;
     const int64_t stride = gridDim.x / 2;
-    const int64_t n_mine = a.n_local > first ? (a.n_local - first + stride - 1) / stride : 0;
+    const int64_t n_super = (a.n_local + MB - 1) / MB;            // super-members of the shard (the last one may be partial)
+    const int64_t n_mine = n_super > first ? (n_super - first + stride - 1) / stride : 0;
 
     if constexpr (kMmaRegs < kLaunchRegs) {            // warpgroup 4 gives registers back only if the budget needs them
         if (warp >= kMmaWarp && warp < kEpiWarp0) reg_dealloc<kMmaRegs>();
@@ -440,29 +452,57 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                     if (lane == 0) TRACE(0, i, 3 + 6 * nc);
                     const uint32_t d = tm + (uint32_t)(C::ACC_BASE + st * kNC);
 #pragma unroll
-                    for (int ka = 0; ka < C::KAT; ++ka) {
-                        const int k = C::NCH + nc * C::KAT + ka;
+                    for (int sx = 0; sx < C::KATC; ++sx) {
+                        const int k = C::NCH + nc * C::KATC + sx;
                         const uint32_t s = ring_slot(k), sph = ring_par(k, (uint32_t)i);
-                        if (nc == 0 && (ka & 1) == 0) mbar_wait(BAR(h_ready, ka >> 1), (uint32_t)i & 1);
+                        // the H1 atoms this slot multiplies must have been written by the epilogue
+                        if (H == 256) {
+                            if (nc == 0 && (sx & 1) == 0) mbar_wait(BAR(h_ready, sx >> 1), (uint32_t)i & 1);
+                        } else if (sx == 0) {
+                            mbar_wait(BAR(h_ready, nc), (uint32_t)i & 1);
+                        }
                         mbar_wait(BAR(slot_full, s), sph);
                         tc_fence_after();
-                        if (lane == 0) TRACE(0, i, 4 + 6 * nc + ka);
+                        if (lane == 0) TRACE(0, i, 4 + 6 * nc + sx);
                         const uint32_t bbase = ring_addr + s * (uint32_t)C::SLOT_BYTES;
                         if (elect_one()) {
+                            if (H >= 128) {
+                                // one 64-wide k atom of this chunk's member: effective atom = the member's column block
+                                const int atom = H == 256 ? sx : 2 * nc + sx;
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                // H1 features 64ka + 16ks .. +16: group g = 2ka + ks/2, hi at column 32g + 8(ks%2), lo 16 further
-                                const uint32_t ah = tm + (uint32_t)(32 * (2 * ka + (ks >> 1)) + 8 * (ks & 1));
-                                const uint64_t bh = smem_desc_sw128(bbase) + (uint64_t)(ks * 2);
-                                mma2_f16_ts(d, ah, bh, idesc, (ka | ks) != 0);
-                                if (X3) {
-                                    const uint64_t bl = smem_desc_sw128(bbase + 8192) + (uint64_t)(ks * 2);
-                                    mma2_f16_ts(d, ah + 16, bh, idesc, 1);      // H1_lo W_hi
-                                    mma2_f16_ts(d, ah, bl, idesc, 1);           // H1_hi W_lo
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    // H1 units 64 atom + 16ks .. +16: group g = 2 atom + ks/2, hi at column 32g + 8(ks%2), lo 16 further
+                                    const uint32_t ah = tm + (uint32_t)(32 * (2 * atom + (ks >> 1)) + 8 * (ks & 1));
+                                    const uint64_t bh = smem_desc_sw128(bbase) + (uint64_t)(ks * 2);
+                                    mma2_f16_ts(d, ah, bh, idesc, (sx | ks) != 0);
+                                    if (X3) {
+                                        const uint64_t bl = smem_desc_sw128(bbase + 8192) + (uint64_t)(ks * 2);
+                                        mma2_f16_ts(d, ah + 16, bh, idesc, 1);      // H1_lo W_hi
+                                        mma2_f16_ts(d, ah, bl, idesc, 1);           // H1_hi W_lo
+                                    }
+                                }
+                            } else {
+                                // H = 64: the slot holds two members' tiles (rows 0-31 / 32-63 of each CTA): two N = 64 products,
+                                // each against its own member's H1 atom, into its own 64 columns of the stage
+                                constexpr uint32_t idesc64 = idesc_f16(256, 64);
+#pragma unroll
+                                for (int g2 = 0; g2 < 2; ++g2) {
+                                    const int atom = 2 * nc + g2;
+#pragma unroll
+                                    for (int ks = 0; ks < 4; ++ks) {
+                                        const uint32_t ah = tm + (uint32_t)(32 * (2 * atom + (ks >> 1)) + 8 * (ks & 1));
+                                        const uint64_t bh = smem_desc_sw128(bbase + g2 * 4096) + (uint64_t)(ks * 2);
+                                        mma2_f16_ts(d + 64 * g2, ah, bh, idesc64, ks != 0);
+                                        if (X3) {
+                                            const uint64_t bl = smem_desc_sw128(bbase + 8192 + g2 * 4096) + (uint64_t)(ks * 2);
+                                            mma2_f16_ts(d + 64 * g2, ah + 16, bh, idesc64, 1);
+                                            mma2_f16_ts(d + 64 * g2, ah, bl, idesc64, 1);
+                                        }
+                                    }
                                 }
                             }
                             mma2_commit(BAR(slot_empty, s));
-                            if (ka == C::KAT - 1) mma2_commit(BAR(acc_full, st));
+                            if (sx == C::KATC - 1) mma2_commit(BAR(acc_full, st));
                         }
                         __syncwarp();
                     }
@@ -475,17 +515,19 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
         // theta of a layer-2 tile does not depend on the member: the 64 x 64 fp32 box of fc2.weight a generator slot needs
         // is refilled into its stage the moment all sixteen generator warps have read the stage's previous box
         if (lane == 0) {
-            const uint32_t total = (uint32_t)n_mine * (uint32_t)(C::NCH * C::KAT);
-            const int row_base = 64 * (int)rank;
-            uint32_t w = 0;                                      // layer-2 slot of the member: (nc, ka) = (w / KAT, w % KAT)
+            const uint32_t total = (uint32_t)n_mine * (uint32_t)C::W2SLOTS;
+            uint32_t w = 0;                                      // layer-2 slot of the super-member: (nc, sx) = (w / KATC, w % KATC)
             for (uint32_t q = 0; q < total; ++q) {
                 const uint32_t stg = q % kThStages, use = q / kThStages;
                 if (use > 0) mbar_wait(BAR(th_empty, stg), (use - 1) & 1);
                 const uint32_t bar = BAR(th_full, stg);
-                mbar_expect_tx(bar, kThetaStage);
-                tma_load_2d(smem_u32(th_stage + stg * kThetaStage), &w2_map, (int)(w % C::KAT) * 64,
-                            (int)(w / C::KAT) * kNC + row_base, bar);
-                if (++w == (uint32_t)(C::NCH * C::KAT)) w = 0;
+                const int nc = (int)(w / C::KATC), sx = (int)(w % C::KATC);
+                // rows of fc2.weight this CTA perturbs in the slot, and the 64 columns (k) of the atom
+                const int row0 = H == 256 ? nc * kNC + 64 * (int)rank : (H == 128 ? 64 * (int)rank : 32 * (int)rank);
+                const int col0 = H == 64 ? 0 : sx * 64;
+                mbar_expect_tx(bar, C::TH_BYTES);
+                tma_load_2d(smem_u32(th_stage + stg * kThetaStage), &w2_map, col0, row0, bar);
+                if (++w == (uint32_t)C::W2SLOTS) w = 0;
             }
         }
     } else if (warp >= kEpiWarp0) {
@@ -504,7 +546,7 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
             const uint32_t p = mi & 1;
             mbar_wait(BAR(s1_full, p), (mi >> 1) & 1);
             if (ew == 0 && lane == 0) TRACE(1, (int64_t)mi, 0);
-            const uint32_t b1 = s1_addr + p * (H * 4);
+            const uint32_t b1 = s1_addr + p * (HH * 4);
             for (int nc = 0; nc < C::NCH; ++nc) {
                 mbar_wait(BAR(d1_full, nc), mi & 1);
                 tc_fence_after();
@@ -552,12 +594,12 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
             if (lane == 0) mbar_arrive(BAR(s1_empty, p));
         };
 
-        float2 actp[A4];                          // (even-n, odd-n) partial sums of action q
+        float2 actp[MC][A4];                      // (even-n, odd-n) partial sums of action q, per member of the chunk
         // ---------------- E2 chunk nc: H2 = tanh(D2 + b2'); a += H2 W3'^T in fp32 registers
         auto epilogue2 = [&](uint32_t p, int nc, int64_t tri) {
             const uint32_t u = acc_u++, st = u & 1, ph = (u >> 1) & 1;
             const uint32_t b2 = s2_addr + p * (uint32_t)(s2_floats * 4);
-            const uint32_t w3 = b2 + H * 4;
+            const uint32_t w3 = b2 + HH * 4;
             mbar_wait(BAR(acc_full, st), ph);
             tc_fence_after();
             if (ew == 0 && lane == 0) TRACE(1, tri, 5 + 2 * nc);
@@ -593,11 +635,12 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                             h23 = make_float2(tanh_fast(x23.x), tanh_fast(x23.y));
                         }
                         // layer 3 (model.py:38) in fp32 on packed FFMA2: W3' row-major [q][n], 4 consecutive n per LDS.128
+                        // (H = 64: the chunk's two members are its two column halves, i.e. this warp's two groups)
 #pragma unroll
                         for (int q = 0; q < A4; ++q) {
-                            const float4 w = lds128(w3 + (q * H + n0) * 4);
-                            actp[q] = ffma2(h01, make_float2(w.x, w.y), actp[q]);
-                            actp[q] = ffma2(h23, make_float2(w.z, w.w), actp[q]);
+                            const float4 w = lds128(w3 + (q * HH + n0) * 4);
+                            actp[MC == 2 ? gi : 0][q] = ffma2(h01, make_float2(w.x, w.y), actp[MC == 2 ? gi : 0][q]);
+                            actp[MC == 2 ? gi : 0][q] = ffma2(h23, make_float2(w.z, w.w), actp[MC == 2 ? gi : 0][q]);
                         }
                     }
                     if (gi == 0) tmem_ld16(acc_base + 32 * (2 + par) + 16 * hf, hf ? vb : va);     // next group
@@ -606,59 +649,84 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
             if (ew == 0 && lane == 0) TRACE(1, tri, 6 + 2 * nc);
         };
 
+        // ---------------- the members completed by chunk nc of super-member (index sm): combine the two warps of the quadrant,
+        // clip, squared error against the tape targets (utils.py:134-137), fixed-order reduction, one atomicAdd per CTA
+        uint32_t fc = 0;                                              // finalize calls so far: buffers / barrier ids alternate
+        auto finalize = [&](uint32_t p, int nc, int64_t sm, bool last) {
+            const uint32_t pb = fc & 1;
+            ++fc;
+            float act[MC][A4];
+#pragma unroll
+            for (int mc = 0; mc < MC; ++mc)
+#pragma unroll
+                for (int q = 0; q < A4; ++q) act[mc][q] = actp[mc][q].x + actp[mc][q].y;
+            if (par == 1) {
+#pragma unroll
+                for (int mc = 0; mc < MC; ++mc)
+#pragma unroll
+                    for (int q = 0; q < A4; ++q) act_x[((pb * 128 + row) * MC + mc) * A4 + q] = act[mc][q];
+                __syncwarp();
+                if (last && lane == 0) mbar_arrive(BAR(s2_empty, p));     // done with this super-member's b2/W3
+                asm volatile("bar.arrive %0, 256;" ::"r"(2 + pb) : "memory");     // ids alternate call by call
+            } else {
+                asm volatile("bar.sync %0, 256;" ::"r"(2 + pb) : "memory");
+#pragma unroll
+                for (int mc = 0; mc < MC; ++mc) {
+                    const int jl = H == 256 ? 0 : (H == 128 ? nc : 2 * nc + mc);        // member inside the super-member
+                    const uint32_t b3 = s2_addr + p * (uint32_t)(s2_floats * 4) + (uint32_t)((HH + A4 * HH + jl * kMaxA) * 4);
+                    float sq = 0.f;
+#pragma unroll
+                    for (int q = 0; q < A4; ++q) {
+                        if (q < L.A) {
+                            float v = (act[mc][q] + act_x[((pb * 128 + row) * MC + mc) * A4 + q]) + lds32(b3 + q * 4);   // even + odd groups
+                            v = fminf(fmaxf(v, -a.clip), a.clip);
+                            const float d = v - tgt_s[row * A4 + q];
+                            sq = __fmaf_rn(d, d, sq);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                    if (lane == 0) bars->fit_part[pb][ew][mc] = sq;
+                }
+                if (last && lane == 0) mbar_arrive(BAR(s2_empty, p));
+                if (ew == 0) {
+                    asm volatile("bar.sync %0, 128;" ::"r"(4 + pb) : "memory");
+                    if (lane < MC) {
+                        const int jl = H == 256 ? 0 : (H == 128 ? nc : 2 * nc + lane);
+                        const int64_t m = sm * MB + jl;
+                        double f = 0.0;
+                        for (int w = 0; w < 4; ++w) f += (double)bars->fit_part[pb][w][lane];
+                        // the pair adds its two halves into the (pre-zeroed) output: two commutative fp32 adds -> deterministic
+                        if (m < a.n_local) atomicAdd(a.fitness + m, (float)(-f));
+                    }
+                } else {
+                    asm volatile("bar.arrive %0, 128;" ::"r"(4 + pb) : "memory");
+                }
+            }
+        };
+        auto zero_actp = [&]() {
+#pragma unroll
+            for (int mc = 0; mc < MC; ++mc)
+#pragma unroll
+                for (int q = 0; q < A4; ++q) actp[mc][q] = make_float2(0.f, 0.f);
+        };
+
         uint32_t mi = 0;
         if (n_mine > 0) epilogue1(0);
         for (int64_t i = 0; i < n_mine; ++i, ++mi) {
-            const int64_t m = first + i * stride;
+            const int64_t sm = first + i * stride;
             const uint32_t p = mi & 1;
             mbar_wait(BAR(s2_full, p), (mi >> 1) & 1);
             if (ew == 0 && lane == 0) TRACE(1, i, 10);
-#pragma unroll
-            for (int q = 0; q < A4; ++q) actp[q] = make_float2(0.f, 0.f);
-            for (int nc = 0; nc < C::NCH - 1; ++nc) epilogue2(p, nc, i);
-            if (i + 1 < n_mine) epilogue1(mi + 1);              // the next member's H1, ahead of this member's last chunk
-            epilogue2(p, C::NCH - 1, i);
-            // ---- member done: combine the two warps of the quadrant, clip, squared error (utils.py:134-137)
-            float act[A4];
-#pragma unroll
-            for (int q = 0; q < A4; ++q) act[q] = actp[q].x + actp[q].y;
-            float sq = 0.f;
-            if (par == 1) {
-#pragma unroll
-                for (int q = 0; q < A4; ++q) act_x[(p * 128 + row) * A4 + q] = act[q];
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(s2_empty, p));     // done with this member's b2/W3
-                asm volatile("bar.arrive %0, 256;" ::"r"(2 + p) : "memory");     // ids alternate with the member parity
-            } else {
-                asm volatile("bar.sync %0, 256;" ::"r"(2 + p) : "memory");
-                const uint32_t b3 = s2_addr + p * (uint32_t)(s2_floats * 4) + (uint32_t)((H + A4 * H) * 4);
-#pragma unroll
-                for (int q = 0; q < A4; ++q) {
-                    if (q < L.A) {
-                        float v = (act[q] + act_x[(p * 128 + row) * A4 + q]) + lds32(b3 + q * 4);     // fixed order: even + odd groups
-                        v = fminf(fmaxf(v, -a.clip), a.clip);
-                        const float d = v - tgt_s[row * A4 + q];
-                        sq = __fmaf_rn(d, d, sq);
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-                if (lane == 0) {
-                    bars->fit_part[p][ew] = sq;
-                    mbar_arrive(BAR(s2_empty, p));
-                }
-                if (ew == 0) {
-                    asm volatile("bar.sync %0, 128;" ::"r"(4 + p) : "memory");
-                    if (lane == 0) {
-                        double f = 0.0;
-                        for (int w = 0; w < 4; ++w) f += (double)bars->fit_part[p][w];
-                        // the pair adds its two halves into the (pre-zeroed) output: two commutative fp32 adds -> deterministic
-                        atomicAdd(a.fitness + m, (float)(-f));
-                    }
-                } else {
-                    asm volatile("bar.arrive %0, 128;" ::"r"(4 + p) : "memory");
-                }
+            zero_actp();
+            epilogue2(p, 0, i);
+            if (H != 256) {                                     // chunk 0 completes its member(s)
+                finalize(p, 0, sm, false);
+                zero_actp();
             }
+            if (i + 1 < n_mine) epilogue1(mi + 1);              // the next super-member's H1, ahead of this one's last chunk
+            epilogue2(p, 1, i);
+            finalize(p, 1, sm, true);
             if (ew == 0 && lane == 0) TRACE(1, i, 9);
         }
     } else if (warp < kGenWarps) {
@@ -682,25 +750,26 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
             const int r = r2 + (64 / kOct) * o;
             oct_off[o] = (uint32_t)(r * 128 + ((c82 ^ (r & 7)) << 4));
         }
-        const int row_base = 64 * (int)rank;                            // this CTA's 64 rows of every 128-row chunk
         // resident theta through 32-bit shared addresses (one register) instead of five generic pointers
         const uint32_t th_base = smem_u32(th_w1);
         const uint32_t th_b1_off = (uint32_t)(C::NCH * 64 * d0p * 4);
         const float bsc = X3 ? kTwoLog2e : 1.0f;     // the f16x3 epilogue evaluates tanh(v + b) as 1 - 2/(1 + 2^(v c + b c))
         uint32_t mi = 0;
         for (int64_t i = 0; i < n_mine; ++i, ++mi) {
-            const uint32_t member = (uint32_t)(a.member_offset + (uint64_t)(first + i * stride));
+            // first member of this super-member (members are GLOBAL ids: the noise is a function of them)
+            const uint32_t member0 = (uint32_t)(a.member_offset + (uint64_t)(first + i * stride) * (uint64_t)MB);
             const uint32_t p = mi & 1;
             if (gtid == 0) TRACE(2, i, 0);
             // The small pieces (thread ranges: kB1Off / kL1Alt / kB2Off / kB3Off above) take their theta from the resident copy.
             // ---- b1' (needed first)
             gen_wait(BAR(s1_empty, p), ((mi >> 1) & 1) ^ 1);
             {
-                const int k = gtid - kB1Off;
-                if (k >= 0 && k < H / 4) {
-                    const float4 v1 = perturbed_quad((uint32_t)((L.off_b1 >> 2) + k), member, gen, kStreamNesEps, a.key,
-                                                     a.neg2ln2_sigma2, lds128(th_base + th_b1_off + (uint32_t)k * 16));
-                    reinterpret_cast<float4 *>(small1 + p * H)[k] = make_float4(v1.x * bsc, v1.y * bsc, v1.z * bsc, v1.w * bsc);
+                const int k = gtid - kB1Off;                              // quad of effective units 4k .. 4k+3
+                if (k >= 0 && k < HH / 4) {
+                    const int jm = (4 * k) / H, fq = ((4 * k) % H) >> 2;       // member, quad of its b1
+                    const float4 v1 = perturbed_quad((uint32_t)((L.off_b1 >> 2) + fq), member0 + (uint32_t)jm, gen, kStreamNesEps, a.key,
+                                                     a.neg2ln2_sigma2, lds128(th_base + th_b1_off + (uint32_t)fq * 16));
+                    reinterpret_cast<float4 *>(small1 + p * HH)[k] = make_float4(v1.x * bsc, v1.y * bsc, v1.z * bsc, v1.w * bsc);
                 }
             }
             __syncwarp();
@@ -712,7 +781,9 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                 gen_wait(BAR(slot_empty, s), sph ^ 1);
                 if ((gtid >> 8) == (kL1Alt ? (nc & 1) : 0)) {   // 64 rows x 4 octets = 256 items
                     const int lt = gtid & 255, r = lt >> 2, c8 = lt & 3;
-                    const int n = nc * kNC + row_base + r;
+                    const int F = nc * kNC + 64 * (int)rank + r;              // effective unit = unit n of member F / H
+                    const int n = F % H;
+                    const uint32_t member = member0 + (uint32_t)(F / H);
                     const uint32_t trow = th_base + (uint32_t)((nc * 64 + r) * d0p * 4);
                     float w[8];
                     if ((L.d0 & 3) == 0) {                                // row starts are quad aligned
@@ -749,19 +820,25 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                 if (lane == 0) arrive_leader(BAR(slot_full, s));
                 if (gtid == 0) TRACE(2, i, 1 + nc);
             }
-            // ---- layer-2 tiles: rows [128nc + 64 rank, +64) x k [64ka, +64) of W2': one octet per thread
+            // ---- layer-2 tiles (the diagonal blocks only): 64 rows x 64 k per CTA and slot, one octet per thread.
+            //      H = 256: rows [128nc + 64 rank, +64) of W2', k atom sx;  H = 128: member nc, rows [64 rank, +64), atom sx;
+            //      H = 64: rows 0-31 of the slot = member 2nc, rows 32-63 = member 2nc+1, each rows [32 rank, +32) of its W2'
 #pragma unroll
             for (int nc = 0; nc < C::NCH; ++nc) {
 #pragma unroll
-                for (int ka = 0; ka < C::KAT; ++ka) {
-                    const int k = C::NCH + nc * C::KAT + ka, w2 = nc * C::KAT + ka;
+                for (int sx = 0; sx < C::KATC; ++sx) {
+                    const int k = C::NCH + nc * C::KATC + sx, w2 = nc * C::KATC + sx;
                     const uint32_t s = ring_slot(k), sph = ring_par(k, mi);
                     const uint32_t stg = (uint32_t)(w2 & 1), tph = th_par(w2, mi);
                     // octet o of this thread: tile row r2 + 32 o (kOct == 2: rows r2 and r2 + 32), k-octet c82
                     BmParts pq[kOct][4];
 #pragma unroll
                     for (int o = 0; o < kOct; ++o) {
-                        const int j0 = L.off_w2 + (nc * kNC + row_base + r2 + (64 / kOct) * o) * H + ka * 64 + c82 * 8;
+                        const int r = r2 + (64 / kOct) * o;
+                        const int jm = H == 256 ? 0 : (H == 128 ? nc : 2 * nc + (r >> 5));
+                        const int fout = H == 256 ? nc * kNC + 64 * (int)rank + r : (H == 128 ? 64 * (int)rank + r : 32 * (int)rank + (r & 31));
+                        const int j0 = L.off_w2 + fout * H + (H == 64 ? 0 : sx * 64) + c82 * 8;
+                        const uint32_t member = member0 + (uint32_t)jm;
                         const uint4 x0 = philox4x32((uint32_t)(j0 >> 2), member, gen, kStreamNesEps, a.key);
                         const uint4 x1 = philox4x32((uint32_t)(j0 >> 2) + 1, member, gen, kStreamNesEps, a.key);
                         pq[o][0] = box_muller_parts(x0.x, x0.y, a.neg2ln2_sigma2);
@@ -773,7 +850,8 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                     float w[kOct][8];
 #pragma unroll
                     for (int o = 0; o < kOct; ++o) {
-                        const uint32_t cell = smem_u32(th_stage + stg * kThetaStage) + (uint32_t)((r2 + (64 / kOct) * o) * 256 + c82 * 32);
+                        const int tr = (r2 + (64 / kOct) * o) & (C::TH_ROWS - 1);           // row of the theta box (H = 64: both members share it)
+                        const uint32_t cell = smem_u32(th_stage + stg * kThetaStage) + (uint32_t)(tr * 256 + c82 * 32);
                         const float4 t0 = lds128(cell), t1 = lds128(cell + 16);
                         w[o][0] = __fmaf_rn(pq[o][0].nr, pq[o][0].c, t0.x); w[o][1] = __fmaf_rn(pq[o][0].nr, pq[o][0].s, t0.y);
                         w[o][2] = __fmaf_rn(pq[o][1].nr, pq[o][1].c, t0.z); w[o][3] = __fmaf_rn(pq[o][1].nr, pq[o][1].s, t0.w);
@@ -788,30 +866,36 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) arrive_leader(BAR(slot_full, s));
-                    if (gtid == 0) TRACE(2, i, 3 + nc * C::KAT + ka);
+                    if (gtid == 0) TRACE(2, i, 3 + nc * C::KATC + sx);
                 }
                 if (nc == 0) {
                     // ---- b2', W3', b3': needed by the epilogue of layer 2, i.e. once the first output chunk has left the tensor pipe
                     gen_wait(BAR(s2_empty, p), ((mi >> 1) & 1) ^ 1);
                     float *sm2 = small2 + p * s2_floats;
-                    for (int k = gtid; k < L.A * H / 4; k += kGenThreads)     // W3' [q][n] row-major: aligned quads
-                        reinterpret_cast<float4 *>(sm2 + H)[k] =
-                            perturbed_quad((uint32_t)((L.off_w3 >> 2) + k), member, gen, kStreamNesEps, a.key, a.neg2ln2_sigma2,
-                                           lds128(th_base + th_b1_off + (uint32_t)(2 * H * 4) + (uint32_t)k * 16));
+                    const uint32_t th_w3_s = th_base + th_b1_off + (uint32_t)(2 * H * 4);
+                    for (int k = gtid; k < L.A * HH / 4; k += kGenThreads) {  // W3' [q][effective unit]: aligned quads
+                        const int qa = k / (HH / 4), F = 4 * (k % (HH / 4));
+                        const int jm = F / H, f = F % H;
+                        reinterpret_cast<float4 *>(sm2 + HH)[k] =
+                            perturbed_quad((uint32_t)((L.off_w3 + qa * H + f) >> 2), member0 + (uint32_t)jm, gen, kStreamNesEps, a.key,
+                                           a.neg2ln2_sigma2, lds128(th_w3_s + (uint32_t)((qa * H + f) * 4)));
+                    }
                     {
-                        const int k = gtid - kB2Off;
-                        if (k >= 0 && k < H / 4) {
-                            const float4 v2 = perturbed_quad((uint32_t)((L.off_b2 >> 2) + k), member, gen, kStreamNesEps, a.key,
-                                                             a.neg2ln2_sigma2, lds128(th_base + th_b1_off + (uint32_t)(H * 4) + (uint32_t)k * 16));
+                        const int k = gtid - kB2Off;                              // quad of effective units 4k .. 4k+3
+                        if (k >= 0 && k < HH / 4) {
+                            const int jm = (4 * k) / H, fq = ((4 * k) % H) >> 2;
+                            const float4 v2 = perturbed_quad((uint32_t)((L.off_b2 >> 2) + fq), member0 + (uint32_t)jm, gen, kStreamNesEps, a.key,
+                                                             a.neg2ln2_sigma2, lds128(th_base + th_b1_off + (uint32_t)(H * 4) + (uint32_t)fq * 16));
                             reinterpret_cast<float4 *>(sm2)[k] = make_float4(v2.x * bsc, v2.y * bsc, v2.z * bsc, v2.w * bsc);
                         }
-                        const int q = gtid - kB3Off;
-                        if (q >= 0 && q < L.A) {
+                        const int t = gtid - kB3Off;                              // b3' of member t / A, action t % A
+                        if (t >= 0 && t < MB * L.A) {
+                            const int jm = t / L.A, q = t - jm * L.A;
                             const int jj = L.off_b3 + q;
-                            const float4 z = noise_quad((uint32_t)(jj >> 2), member, gen, kStreamNesEps, a.key);
+                            const float4 z = noise_quad((uint32_t)(jj >> 2), member0 + (uint32_t)jm, gen, kStreamNesEps, a.key);
                             const int el = jj & 3;
                             const float zz = el == 0 ? z.x : (el == 1 ? z.y : (el == 2 ? z.z : z.w));
-                            sm2[H + A4 * H + q] = __fmaf_rn(a.sigma, zz, lds32(th_base + th_b1_off + (uint32_t)((2 * H + A4 * H + q) * 4)));
+                            sm2[HH + A4 * HH + jm * kMaxA + q] = __fmaf_rn(a.sigma, zz, lds32(th_base + th_b1_off + (uint32_t)((2 * H + A4 * H + q) * 4)));
                         }
                     }
                     __syncwarp();
@@ -858,7 +942,7 @@ static int launch(Args &a, cudaStream_t st) {
     CUtensorMap map;
     const cuuint64_t gdim[2] = {(cuuint64_t)H, (cuuint64_t)H};
     const cuuint64_t gstride[1] = {(cuuint64_t)H * sizeof(float)};
-    const cuuint32_t box[2] = {64, 64};
+    const cuuint32_t box[2] = {64, (cuuint32_t)C::TH_ROWS};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)(a.theta + a.L.off_w2), gdim, gstride, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -868,9 +952,10 @@ static int launch(Args &a, cudaStream_t st) {
         return DES_ERR_CUDA;
     }
     a.a4 = A4;
-    const size_t s2_floats = (size_t)H + (size_t)a.a4 * H + kMaxA;
-    const size_t fixed = 1024 + C::X_TILE_BYTES + kThStages * kThetaStage + (2 * H + 2 * s2_floats) * sizeof(float) + 16 + sizeof(Bars) +
-                         2 * 128 * (size_t)a.a4 * sizeof(float) +
+    constexpr size_t HH = C::HH;
+    const size_t s2_floats = HH + (size_t)a.a4 * HH + C::MB * kMaxA;
+    const size_t fixed = 1024 + C::X_TILE_BYTES + kThStages * kThetaStage + (2 * HH + 2 * s2_floats) * sizeof(float) + 16 + sizeof(Bars) +
+                         2 * 128 * (size_t)C::MC * a.a4 * sizeof(float) +
                          16 + ((size_t)C::NCH * 64 * ((a.L.d0 + 3) & ~3) + 2 * H + (size_t)A4 * H + kMaxA + 128 * A4) * sizeof(float);
     const int n_slots = C::RING;                 // static ring (see Cfg): 5 slots for H = 256, 3 for H = 128
     if (fixed + (size_t)n_slots * C::SLOT_BYTES > 227 * 1024) {
@@ -885,7 +970,8 @@ static int launch(Args &a, cudaStream_t st) {
     DES_CUDA(cudaFuncSetAttribute(eval_pair_kernel<H, X3, A4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // each pair accumulates its two halves into the output with atomicAdd: zero it first
     DES_CUDA(cudaMemsetAsync(a.fitness, 0, (size_t)a.n_local * sizeof(float), st));
-    const int64_t pairs = a.n_local < sms / 2 ? a.n_local : sms / 2;
+    const int64_t n_super = (a.n_local + C::MB - 1) / C::MB;
+    const int64_t pairs = n_super < sms / 2 ? n_super : sms / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * pairs));
     cfg.blockDim = dim3(kThreads);
@@ -937,7 +1023,7 @@ static int launch(Args &a, cudaStream_t st) {
 bool eval_pair_supported(des_dims dims, int precision) {
     const char *e = getenv("DES_TC_PAIR_V2");
     if (e && e[0] == '0') return false;
-    return precision == DES_FWD_F16X3 && (dims.hidden == 128 || dims.hidden == 256) && dims.tape_len == 256 &&
+    return precision == DES_FWD_F16X3 && (dims.hidden == 64 || dims.hidden == 128 || dims.hidden == 256) && dims.tape_len == 256 &&
            dims.state_dim <= pairk::kK1 && dims.action_dim <= pairk::kMaxA;
 }
 
@@ -959,7 +1045,8 @@ int eval_pair_launch(float *fitness, const float *theta, const float *obs, const
     (void)precision;
     const bool wide = dims.action_dim > 4;
     if (dims.hidden == 256) return wide ? launch<256, true, 8>(a, st) : launch<256, true, 4>(a, st);
-    return wide ? launch<128, true, 8>(a, st) : launch<128, true, 4>(a, st);
+    if (dims.hidden == 128) return wide ? launch<128, true, 8>(a, st) : launch<128, true, 4>(a, st);
+    return wide ? launch<64, true, 8>(a, st) : launch<64, true, 4>(a, st);
 }
 
 }  // namespace des
