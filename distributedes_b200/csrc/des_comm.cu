@@ -24,7 +24,7 @@
 namespace des {
 
 constexpr int kMaxWorld = 16;
-constexpr size_t kCommHeader = 1024;      // flags_fit[16] | flags_part[16] | epoch_fit | epoch_part  (u64 each)
+constexpr size_t kCommHeader = 1024;      // flags_fit[16] | flags_part[16] | epoch_fit | epoch_part | fit_done | seg_done[16], all_done (u32)
 
 struct CommDev {
     uint8_t *base[kMaxWorld];             // base[r] = rank r's block as mapped in THIS process
@@ -42,49 +42,72 @@ __device__ __forceinline__ void wait_flag(volatile unsigned long long *f, unsign
     while (*f < epoch) __nanosleep(64);
 }
 
-// one CTA: push the shard to every peer, signal, wait for every peer's signal
+// One CTA per peer: CTA b stores the shard into peer b's fitness_all, raises this rank's flag there, and waits for peer
+// b's flag here — the kernel completes when every peer's shard has landed.  (Round 2, first version: a single CTA pushed to
+// all peers in turn; at 8 GPUs the two exchange kernels were ~60 us of a 1.75 ms generation.)
 __global__ void __launch_bounds__(1024) comm_allgather_fitness_kernel(CommDev c, int64_t offset, int64_t n_local) {
     uint8_t *mine = c.base[c.rank];
-    const float *src = reinterpret_cast<const float *>(mine + c.off_fit) + offset;
-    const unsigned long long epoch = *epoch_fit(mine) + 1;
-    for (int r = 0; r < c.world; ++r) {
-        if (r == c.rank) continue;
-        float *dst = reinterpret_cast<float *>(c.base[r] + c.off_fit) + offset;
+    const int b = blockIdx.x;
+    const unsigned long long epoch = *epoch_fit(mine) + 1;      // every CTA reads it before the last one bumps it (below)
+    if (b != c.rank) {
+        const float *src = reinterpret_cast<const float *>(mine + c.off_fit) + offset;
+        float *dst = reinterpret_cast<float *>(c.base[b] + c.off_fit) + offset;
         for (int64_t i = threadIdx.x; i < n_local; i += blockDim.x) dst[i] = src[i];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < c.world && (int)threadIdx.x != c.rank) {
-        *reinterpret_cast<volatile unsigned long long *>(flags_fit(c.base[threadIdx.x]) + c.rank) = epoch;
-        wait_flag(flags_fit(mine) + threadIdx.x, epoch);
         __threadfence_system();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) *epoch_fit(mine) = epoch;
-}
-
-// one CTA: partial[P] (zero-padded to Ppad) into slot [rank] of every rank's table (its own included), then signal
-__global__ void __launch_bounds__(1024) comm_push_partial_kernel(CommDev c, const float *__restrict__ partial, int64_t P) {
-    uint8_t *mine = c.base[c.rank];
-    const unsigned long long epoch = *epoch_part(mine) + 1;
-    const int64_t nq = c.Ppad / 4;
-    for (int r = 0; r < c.world; ++r) {
-        float4 *dst = reinterpret_cast<float4 *>(c.base[r] + c.off_slots) + (int64_t)c.rank * nq;
-        for (int64_t q = threadIdx.x; q < nq; q += blockDim.x) {
-            float4 v;
-            const int64_t j = 4 * q;
-            v.x = j < P ? partial[j] : 0.f;
-            v.y = j + 1 < P ? partial[j + 1] : 0.f;
-            v.z = j + 2 < P ? partial[j + 2] : 0.f;
-            v.w = j + 3 < P ? partial[j + 3] : 0.f;
-            dst[q] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            *reinterpret_cast<volatile unsigned long long *>(flags_fit(c.base[b]) + c.rank) = epoch;
+            wait_flag(flags_fit(mine) + b, epoch);
+            __threadfence_system();
         }
     }
+    __syncthreads();
+    // the last CTA to finish advances the epoch for the next generation (a device-side counter: graph replay safe)
+    if (threadIdx.x == 0) {
+        unsigned int *done = reinterpret_cast<unsigned int *>(epoch_part(mine) + 1);
+        __threadfence();
+        if (atomicAdd(done, 1u) == gridDim.x - 1) {
+            *done = 0;
+            *epoch_fit(mine) = epoch;
+        }
+    }
+}
+
+// kPushSeg CTAs per peer: CTA (b, seg) stores segment seg of partial[P] (zero-padded to Ppad) into slot [rank] of rank b's
+// table (its own included); the last segment to finish raises this rank's flag at rank b.
+constexpr int kPushSeg = 4;
+__global__ void __launch_bounds__(512) comm_push_partial_kernel(CommDev c, const float *__restrict__ partial, int64_t P) {
+    uint8_t *mine = c.base[c.rank];
+    const int b = blockIdx.x / kPushSeg, seg = blockIdx.x % kPushSeg;
+    const unsigned long long epoch = *epoch_part(mine) + 1;
+    const int64_t nq = c.Ppad / 4;
+    const int64_t q0 = nq * seg / kPushSeg, q1 = nq * (seg + 1) / kPushSeg;
+    float4 *dst = reinterpret_cast<float4 *>(c.base[b] + c.off_slots) + (int64_t)c.rank * nq;
+    for (int64_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+        float4 v;
+        const int64_t j = 4 * q;
+        v.x = j < P ? partial[j] : 0.f;
+        v.y = j + 1 < P ? partial[j + 1] : 0.f;
+        v.z = j + 2 < P ? partial[j + 2] : 0.f;
+        v.w = j + 3 < P ? partial[j + 3] : 0.f;
+        dst[q] = v;
+    }
     __threadfence_system();
     __syncthreads();
-    if ((int)threadIdx.x < c.world)
-        *reinterpret_cast<volatile unsigned long long *>(flags_part(c.base[threadIdx.x]) + c.rank) = epoch;
-    if (threadIdx.x == 0) *epoch_part(mine) = epoch;       // the reduce kernel (same stream) reads it
+    if (threadIdx.x == 0) {
+        unsigned int *seg_done = reinterpret_cast<unsigned int *>(epoch_part(mine) + 2) + b;       // per-peer segment counters
+        unsigned int *all_done = reinterpret_cast<unsigned int *>(epoch_part(mine) + 2) + kMaxWorld;
+        if (atomicAdd(seg_done, 1u) == kPushSeg - 1) {
+            *seg_done = 0;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(flags_part(c.base[b]) + c.rank) = epoch;
+        }
+        if (atomicAdd(all_done, 1u) == gridDim.x - 1) {
+            *all_done = 0;
+            __threadfence();
+            *epoch_part(mine) = epoch;                     // read by the reduce kernel that follows on the stream
+        }
+    }
 }
 
 // partial_sum[j] = sum over ranks r = 0..G-1 (in that order) of slot[r][j], after every rank's flag has arrived
@@ -178,7 +201,7 @@ extern "C" DES_API int des_comm_allgather_fitness(des_comm *c, int64_t member_of
     using namespace des;
     DES_REQUIRE(c && c->connected, "des_comm_allgather_fitness: communicator not connected");
     DES_REQUIRE(member_offset >= 0 && n_local >= 0 && member_offset + n_local <= c->dev.N, "des_comm_allgather_fitness: bad shard");
-    comm_allgather_fitness_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(c->dev, member_offset, n_local);
+    comm_allgather_fitness_kernel<<<c->dev.world, 1024, 0, (cudaStream_t)stream>>>(c->dev, member_offset, n_local);
     DES_LAUNCH_CHECK("comm_allgather_fitness_kernel");
     return DES_OK;
 }
@@ -190,7 +213,7 @@ extern "C" DES_API int des_comm_allreduce_partial(des_comm *c, float *partial_su
     DES_REQUIRE(partial_sum_out_dev && partial_dev && P >= 1 && (P + 3) / 4 * 4 == c->dev.Ppad,
                 "des_comm_allreduce_partial: bad arguments (P=%lld)", (long long)P);
     cudaStream_t st = (cudaStream_t)stream;
-    comm_push_partial_kernel<<<1, 1024, 0, st>>>(c->dev, partial_dev, P);
+    comm_push_partial_kernel<<<c->dev.world * kPushSeg, 512, 0, st>>>(c->dev, partial_dev, P);
     DES_LAUNCH_CHECK("comm_push_partial_kernel");
     comm_reduce_partial_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(c->dev, partial_sum_out_dev, P);
     DES_LAUNCH_CHECK("comm_reduce_partial_kernel");
