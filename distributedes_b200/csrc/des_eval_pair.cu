@@ -841,10 +841,10 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                         const uint32_t member = member0 + (uint32_t)jm;
                         const uint4 x0 = philox4x32((uint32_t)(j0 >> 2), member, gen, kStreamNesEps, a.key);
                         const uint4 x1 = philox4x32((uint32_t)(j0 >> 2) + 1, member, gen, kStreamNesEps, a.key);
-                        pq[o][0] = box_muller_parts(x0.x, x0.y, a.neg2ln2_sigma2);
-                        pq[o][1] = box_muller_parts(x0.z, x0.w, a.neg2ln2_sigma2);
-                        pq[o][2] = box_muller_parts(x1.x, x1.y, a.neg2ln2_sigma2);
-                        pq[o][3] = box_muller_parts(x1.z, x1.w, a.neg2ln2_sigma2);
+                        pq[o][0] = box_muller_parts(x0.x, x0.y, a.neg2ln2_sigma2, a.key.one_bits);
+                        pq[o][1] = box_muller_parts(x0.z, x0.w, a.neg2ln2_sigma2, a.key.one_bits);
+                        pq[o][2] = box_muller_parts(x1.x, x1.y, a.neg2ln2_sigma2, a.key.one_bits);
+                        pq[o][3] = box_muller_parts(x1.z, x1.w, a.neg2ln2_sigma2, a.key.one_bits);
                     }
                     mbar_wait(BAR(th_full, stg), tph);           // this slot's theta box has landed
                     float w[kOct][8];

@@ -686,10 +686,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) eval_tc_kernel(TcArgs a) {
                             }
                             const uint4 x0 = philox4x32((uint32_t)(j0 >> 2), member, gen, kStreamNesEps, a.key);
                             const uint4 x1 = philox4x32((uint32_t)(j0 >> 2) + 1, member, gen, kStreamNesEps, a.key);
-                            const BmParts pa = box_muller_parts(x0.x, x0.y, a.neg2ln2_sigma2);
-                            const BmParts pb = box_muller_parts(x0.z, x0.w, a.neg2ln2_sigma2);
-                            const BmParts pc = box_muller_parts(x1.x, x1.y, a.neg2ln2_sigma2);
-                            const BmParts pd = box_muller_parts(x1.z, x1.w, a.neg2ln2_sigma2);
+                            const BmParts pa = box_muller_parts(x0.x, x0.y, a.neg2ln2_sigma2, a.key.one_bits);
+                            const BmParts pb = box_muller_parts(x0.z, x0.w, a.neg2ln2_sigma2, a.key.one_bits);
+                            const BmParts pc = box_muller_parts(x1.x, x1.y, a.neg2ln2_sigma2, a.key.one_bits);
+                            const BmParts pd = box_muller_parts(x1.z, x1.w, a.neg2ln2_sigma2, a.key.one_bits);
                             if (kStageTheta) {
                                 cp_async_wait<1>();                           // this slot's theta has landed
                                 t0 = *stage_cell(stg, 0);

@@ -70,19 +70,90 @@ __global__ void rank_finish_kernel(float *__restrict__ shaped, int32_t *__restri
 //   4. members are grouped by bucket (order inside a bucket is arbitrary; it does not matter below)
 //   5. rank_i = bucket_start + #{j in bucket : (key_j, j) < (key_i, i)}     — exact, ties by index
 // Degenerate inputs (all keys equal) put everything in one bucket: still exact, cost falls back to n * N.
-constexpr int kBuckets = 1024;          // upper bound; populations up to 256k use 256 buckets / 1024 samples (the sample
-constexpr int kSamples = 4096;          // sort is a single CTA: 36 us at 4096 samples, the largest piece of the rank path)
-constexpr int64_t kBucketMinN = 8192;
+constexpr int kBuckets = 1024;          // upper bound; populations up to 256k use 256 buckets / 1024 samples
+constexpr int kSamples = 4096;
+constexpr int64_t kBucketMinN = 8192;    // populations up to this size use the counting rank (DES_RANK_BUCKET_MIN overrides)
+static int64_t bucket_min_n() {
+    static const int64_t v = [] {
+        const char *e = getenv("DES_RANK_BUCKET_MIN");
+        const long long x = e ? atoll(e) : 0;
+        return x >= 1024 ? (int64_t)x : kBucketMinN;
+    }();
+    return v;
+}
 __host__ __device__ inline int buckets_for(int64_t N) { return N <= 262144 ? 256 : kBuckets; }
 
+// sample t of ns: the key of member floor(t N / ns)   (t < 4096, N < 2^31: the product fits 64 bits)
+__device__ __forceinline__ uint32_t sample_key(const float *__restrict__ fitness, int64_t N, int t, int ns) {
+    return order_key(__ldg(fitness + (int64_t)(((uint64_t)t * (uint64_t)N) / (uint64_t)ns)));
+}
+
+// ascending bitonic sort of 1024 keys, one per thread of a 1024-thread CTA: partner distances below 32 go through
+// shuffles, the 15 wider steps through shared memory.  Returns with s[0..1023] sorted (and a barrier behind it).
+__device__ __forceinline__ void sort1024(uint32_t v, uint32_t *s) {
+    const int t = threadIdx.x;
+    for (int k = 2; k <= 1024; k <<= 1) {
+        const bool up = (t & k) == 0;
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            uint32_t o;
+            if (j >= 32) {
+                s[t] = v;
+                __syncthreads();
+                o = s[t ^ j];
+                __syncthreads();
+            } else {
+                o = __shfl_xor_sync(0xffffffffu, v, j);
+            }
+            const bool keep_min = ((t & j) == 0) == up;
+            v = keep_min ? min(v, o) : max(v, o);
+        }
+    }
+    s[t] = v;
+    __syncthreads();
+}
+
+// bucket(key) = #{splitters <= key}  (monotone in key, so bucket order == key order)
+__device__ __forceinline__ int bucket_of_key(const uint32_t *sp, uint32_t key, int nb) {
+    int lo = 0, hi = nb - 1;                  // answer in [0, nb-1]
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sp[mid] <= key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// 256 buckets (N <= 256k): steps 1+2 in ONE kernel.  Every CTA sorts the same 1024 samples itself (2 us of redundant
+// work instead of a separate single-CTA kernel and a launch dependency), then classifies its 1024 members; the bucket
+// histogram is accumulated in shared memory first (one global atomic per bucket and CTA).
+__global__ void __launch_bounds__(1024) rank_classify256_kernel(int32_t *__restrict__ bucket_count,
+                                                                uint16_t *__restrict__ bucket_id, uint32_t *__restrict__ keys,
+                                                                const float *__restrict__ fitness, int64_t N) {
+    __shared__ uint32_t s[1024];
+    __shared__ uint32_t sp[256];
+    __shared__ int32_t hist[256];
+    const int t = threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * 1024 + t;
+    const uint32_t key = i < N ? order_key(__ldg(fitness + i)) : 0u;
+    if (t < 256) hist[t] = 0;
+    sort1024(sample_key(fitness, N, t, 1024), s);
+    if (t < 255) sp[t] = s[(t + 1) * 4];
+    __syncthreads();
+    if (i < N) {
+        const int b = bucket_of_key(sp, key, 256);
+        keys[i] = key;
+        bucket_id[i] = (uint16_t)b;
+        atomicAdd(hist + b, 1);
+    }
+    __syncthreads();
+    if (t < 256 && hist[t]) atomicAdd(bucket_count + t, hist[t]);
+}
+
+// 1024 buckets (N > 256k): 4096 samples sorted by one CTA (bitonic, shared memory) ...
 __global__ void __launch_bounds__(1024) rank_splitters_kernel(uint32_t *__restrict__ splitters,
                                                               const float *__restrict__ fitness, int64_t N, int nb) {
     __shared__ uint32_t sk[kSamples];
     const int ns = 4 * nb;                   // samples
-    for (int t = threadIdx.x; t < ns; t += 1024) {
-        const int64_t j = (int64_t)(((unsigned __int128)t * (unsigned __int128)N) / ns);
-        sk[t] = order_key(__ldg(fitness + j));
-    }
+    for (int t = threadIdx.x; t < ns; t += 1024) sk[t] = sample_key(fitness, N, t, ns);
     __syncthreads();
     for (int k = 2; k <= ns; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -100,16 +171,7 @@ __global__ void __launch_bounds__(1024) rank_splitters_kernel(uint32_t *__restri
     for (int t = threadIdx.x; t < nb - 1; t += 1024) splitters[t] = sk[(t + 1) * 4];
 }
 
-// bucket(key) = #{splitters <= key}  (monotone in key, so bucket order == key order)
-__device__ __forceinline__ int bucket_of_key(const uint32_t *sp, uint32_t key, int nb) {
-    int lo = 0, hi = nb - 1;                  // answer in [0, nb-1]
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (sp[mid] <= key) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
+// ... and a histogram kernel that reads the splitters back
 __global__ void __launch_bounds__(256) rank_bucket_hist_kernel(int32_t *__restrict__ bucket_count,
                                                                uint16_t *__restrict__ bucket_id, uint32_t *__restrict__ keys,
                                                                const uint32_t *__restrict__ splitters,
@@ -126,58 +188,95 @@ __global__ void __launch_bounds__(256) rank_bucket_hist_kernel(int32_t *__restri
     atomicAdd(bucket_count + b, 1);
 }
 
-__global__ void __launch_bounds__(kBuckets) rank_bucket_scan_kernel(int32_t *__restrict__ bucket_start,
-                                                                    int32_t *__restrict__ bucket_fill,
-                                                                    const int32_t *__restrict__ bucket_count) {
-    __shared__ int32_t s[kBuckets];
-    const int t = threadIdx.x;
-    const int nbk = blockDim.x;
-    s[t] = bucket_count[t];
-    __syncthreads();
-    for (int o = 1; o < nbk; o <<= 1) {               // Hillis-Steele inclusive scan
-        const int32_t v = (t >= o) ? s[t - o] : 0;
-        __syncthreads();
-        s[t] += v;
-        __syncthreads();
-    }
-    bucket_start[t] = s[t] - bucket_count[t];
-    bucket_fill[t] = 0;
-}
-
+// steps 3+4: every CTA scans the (<= 1024) bucket counts itself, CTA 0 publishes the starts, then the members are
+// scattered to their buckets.  bucket_fill must be zero on entry (one memset covers it together with bucket_count).
 __global__ void __launch_bounds__(256) rank_bucket_group_kernel(uint32_t *__restrict__ g_key, int32_t *__restrict__ g_idx,
                                                                 int32_t *__restrict__ bucket_fill,
-                                                                const int32_t *__restrict__ bucket_start,
+                                                                int32_t *__restrict__ bucket_start,
+                                                                const int32_t *__restrict__ bucket_count,
                                                                 const uint16_t *__restrict__ bucket_id,
-                                                                const uint32_t *__restrict__ keys, int64_t N) {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+                                                                const uint32_t *__restrict__ keys, int64_t N, int nb) {
+    __shared__ int32_t start[kBuckets];
+    __shared__ int32_t warp_tot[8];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int per = nb / 256;                        // 1 or 4 consecutive buckets per thread
+    int32_t c[4] = {0, 0, 0, 0}, tot = 0;
+    for (int q = 0; q < per; ++q) { c[q] = bucket_count[t * per + q]; tot += c[q]; }
+    int32_t inc = tot;                               // inclusive scan of the per-thread totals
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    int32_t base = inc - tot;
+    for (int q = 0; q < w; ++q) base += warp_tot[q];
+    for (int q = 0; q < per; ++q) {
+        start[t * per + q] = base;
+        if (blockIdx.x == 0) bucket_start[t * per + q] = base;
+        base += c[q];
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * 256 + t;
     if (i >= N) return;
     const int b = bucket_id[i];
-    const int pos = bucket_start[b] + atomicAdd(bucket_fill + b, 1);
+    const int pos = start[b] + atomicAdd(bucket_fill + b, 1);
     g_key[pos] = keys[i];
     g_idx[pos] = (int32_t)i;
 }
 
+// step 5, by POSITION in the grouped array: a CTA takes 256 consecutive grouped members (a few neighbouring buckets),
+// stages the union of their buckets in shared memory tile by tile and counts, for each member of the shard, the
+// entries of its own bucket that sort before it.  No dependent global loads in the counting loop; in the degenerate
+// all-equal case (one bucket) the N x N comparisons are still spread over all CTAs.
+constexpr int kFinishTile = 1024;
 __global__ void __launch_bounds__(256) rank_bucket_finish_kernel(float *__restrict__ shaped, int32_t *__restrict__ rank_out,
                                                                  const uint32_t *__restrict__ g_key,
                                                                  const int32_t *__restrict__ g_idx,
                                                                  const int32_t *__restrict__ bucket_start,
                                                                  const int32_t *__restrict__ bucket_count,
-                                                                 const uint16_t *__restrict__ bucket_id,
-                                                                 const uint32_t *__restrict__ keys, int64_t N,
+                                                                 const uint16_t *__restrict__ bucket_id, int64_t N,
                                                                  int64_t member_offset, int64_t n_local) {
-    const int64_t il = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (il >= n_local) return;
-    const int64_t ig = member_offset + il;
-    const int b = bucket_id[ig];
-    const int start = bucket_start[b], cnt = bucket_count[b];
-    const uint64_t mine = ((uint64_t)keys[ig] << 32) | (uint64_t)(uint32_t)ig;
-    int32_t r = start;
-    for (int t = 0; t < cnt; ++t) {
-        const uint64_t other = ((uint64_t)__ldg(g_key + start + t) << 32) | (uint64_t)(uint32_t)__ldg(g_idx + start + t);
-        r += (other < mine) ? 1 : 0;
+    __shared__ uint64_t tile[kFinishTile];
+    __shared__ int32_t range[2];
+    const int t = threadIdx.x;
+    const int64_t p = (int64_t)blockIdx.x * 256 + t;
+    if (t == 0) { range[0] = 0x7FFFFFFF; range[1] = 0; }
+    int32_t idx = 0, st = 0, en = 0;
+    uint64_t mine = 0;
+    bool local = false;
+    if (p < N) {
+        idx = g_idx[p];
+        local = idx >= member_offset && idx < member_offset + n_local;
+        if (local) {
+            const int b = bucket_id[idx];
+            st = bucket_start[b];
+            en = st + bucket_count[b];
+            mine = ((uint64_t)g_key[p] << 32) | (uint64_t)(uint32_t)idx;
+        }
     }
-    if (rank_out) rank_out[il] = r;
-    shaped[il] = (float)((double)r / (double)(N - 1) - 0.5);
+    __syncthreads();
+    if (local) { atomicMin(range + 0, st); atomicMax(range + 1, en); }
+    __syncthreads();
+    const int32_t lo = range[0], hi = range[1];
+    int32_t r = st;
+    for (int32_t base = lo; base < hi; base += kFinishTile) {
+        const int n = min(kFinishTile, hi - base);
+        __syncthreads();
+        for (int q = t; q < n; q += 256)
+            tile[q] = ((uint64_t)__ldg(g_key + base + q) << 32) | (uint64_t)(uint32_t)__ldg(g_idx + base + q);
+        __syncthreads();
+        if (local) {
+            const int a = max(st, base) - base, e = min(en, base + n) - base;
+#pragma unroll 4
+            for (int q = a; q < e; ++q) r += (tile[q] < mine) ? 1 : 0;
+        }
+    }
+    if (local) {
+        const int64_t il = idx - member_offset;
+        if (rank_out) rank_out[il] = r;
+        shaped[il] = (float)((double)r / (double)(N - 1) - 0.5);
+    }
 }
 
 struct BucketWs {        // carved out of the caller's workspace (all 16-byte aligned)
@@ -194,9 +293,9 @@ static BucketWs carve(void *ws, int64_t N) {
     uint8_t *p = (uint8_t *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     BucketWs w;
     w.splitters = (uint32_t *)p; p += al(kBuckets * 4);
-    w.bucket_count = (int32_t *)p; p += al(kBuckets * 4);
-    w.bucket_start = (int32_t *)p; p += al(kBuckets * 4);
+    w.bucket_count = (int32_t *)p; p += al(kBuckets * 4);          // count and fill adjacent: one memset
     w.bucket_fill = (int32_t *)p; p += al(kBuckets * 4);
+    w.bucket_start = (int32_t *)p; p += al(kBuckets * 4);
     w.keys = (uint32_t *)p; p += al((size_t)N * 4);
     w.g_key = (uint32_t *)p; p += al((size_t)N * 4);
     w.g_idx = (int32_t *)p; p += al((size_t)N * 4);
@@ -212,7 +311,7 @@ extern "C" DES_API size_t des_rank_workspace_bytes(int64_t n_local) {
 }
 extern "C" DES_API size_t des_rank_workspace_bytes_n(int64_t N, int64_t n_local) {
     const size_t base = des_rank_workspace_bytes(n_local);
-    return N > des::kBucketMinN ? (base > des::bucket_ws_bytes(N) ? base : des::bucket_ws_bytes(N)) : base;
+    return N > des::bucket_min_n() ? (base > des::bucket_ws_bytes(N) ? base : des::bucket_ws_bytes(N)) : base;
 }
 
 extern "C" DES_API int des_centered_rank(float *shaped_out_dev, int32_t *rank_out_dev, const float *fitness_all_dev, int64_t N,
@@ -232,18 +331,22 @@ extern "C" DES_API int des_centered_rank(float *shaped_out_dev, int32_t *rank_ou
         return DES_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (N > kBucketMinN && workspace_bytes >= bucket_ws_bytes(N)) {
+    if (N > bucket_min_n() && workspace_bytes >= bucket_ws_bytes(N)) {
         const BucketWs w = carve(workspace_dev, N);
         const unsigned gn = (unsigned)((N + 255) / 256);
-        DES_CUDA(cudaMemsetAsync(w.bucket_count, 0, kBuckets * sizeof(int32_t), st));
+        DES_CUDA(cudaMemsetAsync(w.bucket_count, 0, 2 * kBuckets * sizeof(int32_t), st));
         const int nb = buckets_for(N);
-        rank_splitters_kernel<<<1, 1024, 0, st>>>(w.splitters, fitness_all_dev, N, nb);
-        rank_bucket_hist_kernel<<<gn, 256, 0, st>>>(w.bucket_count, w.bucket_id, w.keys, w.splitters, fitness_all_dev, N, nb);
-        rank_bucket_scan_kernel<<<1, nb, 0, st>>>(w.bucket_start, w.bucket_fill, w.bucket_count);
-        rank_bucket_group_kernel<<<gn, 256, 0, st>>>(w.g_key, w.g_idx, w.bucket_fill, w.bucket_start, w.bucket_id, w.keys, N);
-        rank_bucket_finish_kernel<<<(unsigned)((n_local + 255) / 256), 256, 0, st>>>(
-            shaped_out_dev, rank_out_dev, w.g_key, w.g_idx, w.bucket_start, w.bucket_count, w.bucket_id, w.keys, N,
-            member_offset, n_local);
+        if (nb == 256) {
+            rank_classify256_kernel<<<(unsigned)((N + 1023) / 1024), 1024, 0, st>>>(w.bucket_count, w.bucket_id, w.keys,
+                                                                                   fitness_all_dev, N);
+        } else {
+            rank_splitters_kernel<<<1, 1024, 0, st>>>(w.splitters, fitness_all_dev, N, nb);
+            rank_bucket_hist_kernel<<<gn, 256, 0, st>>>(w.bucket_count, w.bucket_id, w.keys, w.splitters, fitness_all_dev, N, nb);
+        }
+        rank_bucket_group_kernel<<<gn, 256, 0, st>>>(w.g_key, w.g_idx, w.bucket_fill, w.bucket_start, w.bucket_count,
+                                                     w.bucket_id, w.keys, N, nb);
+        rank_bucket_finish_kernel<<<gn, 256, 0, st>>>(shaped_out_dev, rank_out_dev, w.g_key, w.g_idx, w.bucket_start,
+                                                      w.bucket_count, w.bucket_id, N, member_offset, n_local);
         DES_LAUNCH_CHECK("rank_bucket kernels");
         return DES_OK;
     }

@@ -190,6 +190,34 @@ def test_centered_rank_ties_nan_zero_and_shards():
         ops().centered_rank(torch.zeros(1, device=DEV))                       # N=1: utils.py:146 divides by 0
 
 
+@pytest.mark.parametrize('N,kind', [(8193, 'ties'), (20000, 'equal'), (40001, 'few'), (65536, 'nan'), (300001, 'randn')])
+def test_centered_rank_bucket_path_edge_cases(N, kind):
+    """The bucketed rank (N > 8192): heavy ties, one bucket holding everything, a handful of distinct values, NaN / inf,
+    sizes that are not a multiple of any tile, the 1024-bucket path, and shards against the whole population."""
+    rs = np.random.RandomState(N)
+    f = rs.randn(N).astype(np.float32)
+    if kind == 'ties':
+        f[::3] = f[1]
+    elif kind == 'equal':
+        f[:] = 2.5
+    elif kind == 'few':
+        f = rs.randint(0, 5, N).astype(np.float32)
+    elif kind == 'nan':
+        f[rs.randint(0, N, 100)] = np.nan
+        f[rs.randint(0, N, 100)] = np.inf
+        f[rs.randint(0, N, 100)] = -np.inf
+        f[rs.randint(0, N, 100)] = -0.0
+        f[rs.randint(0, N, 100)] = 0.0
+    full = orc.ranks_stable(f)
+    ft = torch.from_numpy(f).to(DEV)
+    shaped, r = ops().centered_rank(ft, return_ranks=True)
+    assert np.array_equal(r.cpu().numpy(), full)
+    assert np.max(np.abs(shaped.cpu().numpy().astype(np.float64) - orc.fitness_shift(f))) <= 6e-8
+    for off, n in [(0, 1), (N - 1, 1), (N // 8, N // 8), (N // 2 + 3, 1000)]:
+        _, r = ops().centered_rank(ft, member_offset=off, n_local=n, return_ranks=True)
+        assert np.array_equal(r.cpu().numpy(), full[off:off + n])
+
+
 @pytest.mark.parametrize('n_local,P,off', [(16, 4481, 0), (4096, 6020, 0), (300, 73220, 5000), (33, 10, 0), (1, 5, 3)])
 def test_grad_partial_matches_oracle(n_local, P, off):
     rs = np.random.RandomState(1)
