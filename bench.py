@@ -539,6 +539,45 @@ def parity_check(torch, dist, eng, world, dev):
     return res
 
 
+
+def cma_roofline(n, lam, lam_local, world):
+    """Roofline of the rank-mu update's two kernels, timed separately on this rank (CUDA events): the SYRK
+    (tensor pipe when ops picks the split-fp16 tcgen05 path, fp32 CUDA cores below ops.CMA_TC_MIN_N) and the
+    HBM-bound covariance blend.  Flops counted as 2 lambda n^2 (the full square; the kernels compute the upper triangle)."""
+    import torch
+    from distributedes_b200 import ops
+    hbm_peak, bf16_peak, _, peak_kind = peaks()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    Y = torch.randn(lam_local, n, device=dev); w = torch.rand(lam_local, device=dev)
+    Cm = torch.eye(n, device=dev); pc = torch.randn(n, device=dev)
+    dC = ops.cma_rank_mu(Y, w)
+    for _ in range(3):
+        ops.cma_rank_mu(Y, w, out=dC); ops.cma_cov_apply(Cm, dC, pc, decay=0.99, c1=0.001, cmu=0.009)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    for _ in range(10):
+        ops.cma_rank_mu(Y, w, out=dC)
+    ev[1].record()
+    for _ in range(10):
+        ops.cma_cov_apply(Cm, dC, pc, decay=0.99, c1=0.001, cmu=0.009)
+    ev[2].record()
+    torch.cuda.synchronize()
+    t_mu, t_cov = ev[0].elapsed_time(ev[1]) / 10, ev[1].elapsed_time(ev[2]) / 10
+    tc = n >= ops.CMA_TC_MIN_N
+    tf = 2.0 * lam_local * n * n / (t_mu * 1e-3) / 1e12
+    peak = bf16_peak if tc else FP32_FFMA_TFLOPS
+    gbs = 12.0 * n * n / (t_cov * 1e-3) / 1e9
+    return {'kernel': 'des_cma_rank_mu_tc (split-fp16 tcgen05 SYRK, TMA-fed)' if tc else 'des_cma_rank_mu (fp32 FFMA)',
+            'bound': 'tensor' if tc else 'fp32 CUDA cores', 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s',
+            'frac': tf / peak if peak else None,
+            'peak_kind': ('of %s bf16 burst (cuBLAS)' % peak_kind) if tc else 'nominal 148 x 128 FFMA/clk x 1.965 GHz',
+            'tensor_issued_frac': (3.0 * 0.5 * (1 + 256.0 / n) * tf / peak) if (tc and peak) else None,
+            'kernel_ms': t_mu, 'members_this_rank': lam_local, 'n_gpus': world,
+            'note': 'flops counted as 2 lambda n^2; the kernel issues three MMAs per k-step over the 128x256 tiles that touch the upper triangle',
+            'cov_apply': {'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak if hbm_peak else None,
+                          'kernel_ms': t_cov, 'algorithmic_bytes': 12.0 * n * n}}
+
+
 def measure_cma(torch, dist, timed, max_over_ranks, world, rank, dev, hbm_peak, with_cpu):
     """CMA-ES lines: (a) BASELINE configs[2]: whole generations (ask, evaluate sphere, tell) at n=1024, lambda=256 on this
     GPU; (b) configs[4]: the rank-mu covariance update at n=4096, lambda=1024 — shard partial on each GPU, all-reduce of
@@ -576,12 +615,8 @@ def measure_cma(torch, dist, timed, max_over_ranks, world, rank, dev, hbm_peak, 
         r = {'workload': 'cma_es sphere n=%d lambda=%d (BASELINE configs[2])' % (n, lam), 'config_of': 'BASELINE configs[2]',
              'n_gpus': 1, 'generation_ms': gen_ms, 'generations_per_sec': 1e3 / gen_ms,
              'rank_mu_update_ms': upd_ms, 'updates_per_sec': 1e3 / upd_ms,
-             'roofline': {'kernel': 'des_cma_rank_mu + des_cma_cov_apply', 'bound': 'fp32 CUDA cores',
-                          'achieved': flops / (upd_ms * 1e-3) / 1e12, 'peak': FP32_FFMA_TFLOPS, 'unit': 'TFLOP/s',
-                          'frac': flops / (upd_ms * 1e-3) / 1e12 / FP32_FFMA_TFLOPS,
-                          'peak_kind': 'nominal fp32 FFMA (flops counted as 2 lambda n^2, full square)',
-                          'algorithmic_bytes': 8.0 * n * n + 4.0 * lam * n},
-             'parity': 'unpinned: pycma is absent; checked against oracle/cma_oracle.py (tutorial restatement)'}
+             'roofline': cma_roofline(n, lam, lam, 1),
+             'parity': 'oracle/cma_oracle.py (tutorial restatement) pinned by tests/test_cma_pinning.py: constants by hand from Hansen 2016, pycma banner (mu_w, w_1) values, one generation in n=3 by literal arithmetic; pycma itself is absent; kernels vs the restatement <= 1e-5 (tests/test_gpu_cma.py)'}
         if with_cpu and rank == 0:
             r['cpu_baseline'] = cma_cpu_baseline(n, lam)
         out.append(r)
@@ -614,11 +649,8 @@ def measure_cma(torch, dist, timed, max_over_ranks, world, rank, dev, hbm_peak, 
     r = {'workload': 'cma rank-mu covariance update n=%d lambda=%d over %d GPU(s) (BASELINE configs[4])' % (n, lam, world),
          'config_of': 'BASELINE configs[4]', 'n_gpus': world, 'rank_mu_update_ms': upd_ms, 'updates_per_sec': 1e3 / upd_ms,
          'collective': None if world == 1 else 'all-reduce of the packed upper-triangular tiles (%d MB)' % (2 * n * n // (1 << 20) + 1),
-         'roofline': {'kernel': 'des_cma_rank_mu[_packed] + all-reduce + des_cma_cov_apply', 'bound': 'fp32 CUDA cores',
-                      'achieved': flops / (upd_ms * 1e-3) / 1e12, 'peak': FP32_FFMA_TFLOPS * world, 'unit': 'TFLOP/s',
-                      'frac': flops / (upd_ms * 1e-3) / 1e12 / (FP32_FFMA_TFLOPS * world),
-                      'peak_kind': 'nominal fp32 FFMA x GPUs (flops counted as 2 lambda n^2, full square)'},
-         'parity': 'unpinned: pycma is absent; checked against oracle/cma_oracle.py (tutorial restatement)'}
+         'roofline': cma_roofline(n, lam, nl, world),
+         'parity': 'oracle/cma_oracle.py (tutorial restatement) pinned by tests/test_cma_pinning.py: constants by hand from Hansen 2016, pycma banner (mu_w, w_1) values, one generation in n=3 by literal arithmetic; pycma itself is absent; kernels vs the restatement <= 1e-5 (tests/test_gpu_cma.py)'}
     if with_cpu and rank == 0 and world == 1:
         r['cpu_baseline'] = cma_cpu_baseline(n, lam)
     out.append(r)

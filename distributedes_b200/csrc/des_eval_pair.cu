@@ -780,7 +780,9 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                 const uint32_t s = ring_slot(nc), sph = ring_par(nc, mi);
                 gen_wait(BAR(slot_empty, s), sph ^ 1);
                 if ((gtid >> 8) == (kL1Alt ? (nc & 1) : 0)) {   // 64 rows x 4 octets = 256 items
-                    const int lt = gtid & 255, r = lt >> 2, c8 = lt & 3;
+                    // a quarter warp (one STS.128 wavefront) = 4 octets of row r and 4 of row r + 4: the swizzle puts them in
+                    // disjoint 16-byte bank groups (rows r and r + 1 would share them: the tile uses only half of each 128 B row)
+                    const int lt = gtid & 255, c8 = lt & 3, r = (lt >> 5) * 8 + ((lt >> 2) & 1) * 4 + ((lt >> 3) & 3);
                     const int F = nc * kNC + 64 * (int)rank + r;              // effective unit = unit n of member F / H
                     const int n = F % H;
                     const uint32_t member = member0 + (uint32_t)(F / H);

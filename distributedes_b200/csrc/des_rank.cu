@@ -72,7 +72,7 @@ __global__ void rank_finish_kernel(float *__restrict__ shaped, int32_t *__restri
 // Degenerate inputs (all keys equal) put everything in one bucket: still exact, cost falls back to n * N.
 constexpr int kBuckets = 1024;          // upper bound; populations up to 256k use 256 buckets / 1024 samples
 constexpr int kSamples = 4096;
-constexpr int64_t kBucketMinN = 8192;    // populations up to this size use the counting rank (DES_RANK_BUCKET_MIN overrides)
+constexpr int64_t kBucketMinN = 2048;    // populations up to this size use the counting rank (DES_RANK_BUCKET_MIN overrides)
 static int64_t bucket_min_n() {
     static const int64_t v = [] {
         const char *e = getenv("DES_RANK_BUCKET_MIN");

@@ -263,7 +263,7 @@ def nes_apply(theta, adam_m, adam_v, partial_sum, N, state, *, sigma, learning_r
 
 
 _CMA_WS = {}      # (device, n, lambda) -> workspace tensor of the tensor-core rank-mu path
-CMA_TC_MIN_N = 256
+CMA_TC_MIN_N = 2048
 
 
 def _cma_tc_workspace(n, lam, device):

@@ -177,7 +177,7 @@ DES_API int des_pop_eval(float *fitness_out_dev, const float *solutions_dev, con
  * NaN ranks last) and shaped_out_dev[i] = fp32(rank/(N-1) - 0.5).  Replaces fitness_shift
  * utils.py:142-148 (whose argsort is unstable on ties; identical on tie-free input).
  * rank_out_dev may be NULL.  N >= 2.  workspace: at least des_rank_workspace_bytes(n_local); with
- * des_rank_workspace_bytes_n(N, n_local) bytes, populations above 8192 use the bucketed (sample-sort style)
+ * des_rank_workspace_bytes_n(N, n_local) bytes, populations above 2048 use the bucketed (sample-sort style)
  * path whose cost is ~N*N/1024 instead of n_local*N compares.  Results are identical either way. */
 DES_API size_t des_rank_workspace_bytes(int64_t n_local);
 DES_API size_t des_rank_workspace_bytes_n(int64_t N, int64_t n_local);

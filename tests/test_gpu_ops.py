@@ -190,9 +190,9 @@ def test_centered_rank_ties_nan_zero_and_shards():
         ops().centered_rank(torch.zeros(1, device=DEV))                       # N=1: utils.py:146 divides by 0
 
 
-@pytest.mark.parametrize('N,kind', [(8193, 'ties'), (20000, 'equal'), (40001, 'few'), (65536, 'nan'), (300001, 'randn')])
+@pytest.mark.parametrize('N,kind', [(2049, 'ties'), (8193, 'ties'), (20000, 'equal'), (40001, 'few'), (65536, 'nan'), (300001, 'randn')])
 def test_centered_rank_bucket_path_edge_cases(N, kind):
-    """The bucketed rank (N > 8192): heavy ties, one bucket holding everything, a handful of distinct values, NaN / inf,
+    """The bucketed rank (N > 2048): heavy ties, one bucket holding everything, a handful of distinct values, NaN / inf,
     sizes that are not a multiple of any tile, the 1024-bucket path, and shards against the whole population."""
     rs = np.random.RandomState(N)
     f = rs.randn(N).astype(np.float32)
