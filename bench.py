@@ -324,7 +324,26 @@ def run_ours(a):
                            out=eng.fitness_all[eng.offset:eng.offset + eng.n_local], workspace=eng.eval_ws)
         for _ in range(2):
             eval_only()
-        ev_ms, _ = timed(eval_only, steps)
+        # The kernel is timed INSIDE eager generations (events around the launch, the rest of the generation behind it): the
+        # host runs ahead during the long kernels, so no launch latency is billed to the kernel, and the kernel runs under the
+        # power / clock conditions of the step it is a share of.  (Timed in a loop of its own — nothing but this kernel,
+        # back to back — the same launch takes ~5 % longer: the GPU sits at its power cap.)
+        def step_with_eval_events(s_ev, e_ev):
+            if eng.world > 1 and eng.comm is None:
+                eng.fitness_all.zero_()
+            s_ev.record()
+            eval_only()
+            e_ev.record()
+            eng._gather_fitness()
+            eng.rank_and_reduce()
+            eng.apply()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for s_ev, e_ev in evs:
+            flush.zero_()
+            step_with_eval_events(s_ev, e_ev)
+        barrier()
+        ev_ms = float(np.sum([s_ev.elapsed_time(e_ev) for s_ev, e_ev in evs]))
         ev_ms = max_over_ranks(ev_ms) / steps
         alg_bytes = 8.0 * eng.n_local * P                                  # write eps once + read it in the forward
         fwd_flops = 2.0 * eng.n_local * T * (d0 * H + H * H + H * A)

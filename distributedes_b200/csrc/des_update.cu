@@ -14,7 +14,15 @@
 
 namespace des {
 
-constexpr int kGradThreads = 128;
+#ifndef DES_GRAD_THREADS
+#define DES_GRAD_THREADS 128
+#endif
+constexpr int kGradThreads = DES_GRAD_THREADS;
+// members per trip of the inner loop: 1: 3.01 ms, 2: 2.92, 4: 2.78, 8: 2.78 (pop 65 536, P = 73 220; 32 registers throughout)
+#ifndef DES_GRAD_UNROLL
+#define DES_GRAD_UNROLL 4
+#endif
+constexpr int kGradUnroll = DES_GRAD_UNROLL;
 
 struct GradPlan {
     int64_t nq;        // quads = ceil(P/4)
@@ -54,7 +62,7 @@ __global__ void __launch_bounds__(kGradThreads) grad_chunk_kernel(float *__restr
     const int64_t i0 = (int64_t)blockIdx.y * per_chunk;
     const int64_t i1 = min(n_local, i0 + per_chunk);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
+#pragma unroll kGradUnroll
     for (int64_t i = i0; i < i1; ++i) {
         const float s = __ldg(shaped + i);     // warp-uniform broadcast load
         const uint4 x = philox4x32((uint32_t)q, (uint32_t)(member_offset + i), gen, kStreamNesEps, key);
