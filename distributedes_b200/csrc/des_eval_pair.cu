@@ -56,6 +56,25 @@ constexpr int kGenThreads = kGenWarps * 32;
 constexpr int kOct = 512 / kGenThreads;                // octets of a 64 x 64 tile per generator thread
 static_assert(kGenWarps == 16 || kGenWarps == 8, "generator warps: 16 or 8");
 constexpr int kEpiWarps = 8;
+// DES_PAIR_GEN_E1 = 16-column units of a chunk's eight that the generator warps of a lane quadrant take over from the
+// layer-1 epilogue when H < 256 (0, 2 or 4).  At H = 64 / 128 the super-member pipeline is epilogue-bound (the epilogue
+// handles 256 effective units per super-member whatever H is, the generators only the diagonal blocks of layer 2: they
+// wait more than half of the time), so the generators help right after they have produced the layer-1 tiles — the point
+// where they would wait for that very layer-1 MMA.  At H = 256 both roles are saturated and the same hand-over costs
+// 6 % (profiles/README.md): there the epilogue keeps all eight units.  H1 is laid out in 16-column UNITS (fp16 hi pairs in
+// columns [16u, 16u+8), lo pairs in [16u+8, 16u+16)) so that a unit is read and written back by one warp alone.
+// Measured (pop 4096 / H = 64 and pop 16 384 / H = 128): 0 units 0.130 / 0.966 ms, 2: 0.132 / 0.988, 4: 0.126 / 0.910.
+#ifndef DES_PAIR_GEN_E1_H64
+#define DES_PAIR_GEN_E1_H64 4
+#endif
+#ifndef DES_PAIR_GEN_E1_H128
+#define DES_PAIR_GEN_E1_H128 4
+#endif
+template <int H>
+struct GenE1 {
+    static constexpr int value = H == 256 ? 0 : (H == 64 ? DES_PAIR_GEN_E1_H64 : DES_PAIR_GEN_E1_H128);
+    static_assert(value == 0 || value == 2 || value == 4 || value == 8, "generator units per chunk: 0, 2, 4 or 8");
+};
 constexpr int kMmaWarp = kGenWarps;            // warpgroup 4: MMA issuer, TMA producer, two idle warps
 constexpr int kProdWarp = kMmaWarp + 1;
 constexpr int kEpiWarp0 = kGenWarps + 4;       // warpgroups 5-6
@@ -239,6 +258,26 @@ constexpr int kTrFirst = 16, kTrMembers = 8, kTrEvents = 16;      // members (pe
 #define TRACE(role, i, ev) do { } while (0)
 #endif
 
+// One 16-column unit of the layer-1 epilogue: v = D1[row, 16u .. 16u+16) (already in registers) -> tanh(v + b1') ->
+// fp16 hi pairs in columns [16u, 16u+8), lo pairs in [16u+8, 16u+16) of the same TMEM columns (one tcgen05.st).
+// bias_s: shared address of the 16 pre-scaled biases of the unit.
+template <bool X3>
+__device__ __forceinline__ void e1_unit(uint32_t taddr, uint32_t bias_s, const uint32_t (&v)[16]) {
+    static_assert(X3, "the unit layout carries hi and lo halves");
+    uint32_t out[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 b = lds128(bias_s + 16 * i);
+        const float2 v01 = make_float2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]));
+        const float2 v23 = make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        float2 t01, t23;
+        tanh4(v01, v23, b, t01, t23);
+        split_h2p(t01, out[2 * i], out[8 + 2 * i]);
+        split_h2p(t23, out[2 * i + 1], out[8 + 2 * i + 1]);
+    }
+    tmem_st16(taddr, out);
+}
+
 // one lane of a fully converged warp (the issuing lane of the MMA role)
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -285,6 +324,8 @@ __device__ __forceinline__ void store_octet_s(uint32_t slot_addr_plus_off, const
 template <int H, bool X3, int A4>
 __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_constant__ CUtensorMap w2_map) {
     using C = Cfg<H, X3>;
+    constexpr int GE = GenE1<H>::value;               // units per chunk taken by the generator warps of a quadrant
+    constexpr int kEpiUnits = (8 - GE) / 2;           // ... and by each of the two epilogue warps
     const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -330,7 +371,7 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                 mbar_init(smem_u32(&bars->s2_full[p]), kGenWarps);
                 mbar_init(smem_u32(&bars->s2_empty[p]), kEpiWarps);
                 mbar_init(smem_u32(&bars->d1_full[p]), 1);
-                mbar_init(smem_u32(&bars->h_ready[p]), 2 * kEpiWarps);
+                mbar_init(smem_u32(&bars->h_ready[p]), 2 * (kEpiWarps + (GE >= 4 ? kGenWarps : GE * kGenWarps / 4)));   // one arrival per participating warp
                 mbar_init(smem_u32(&bars->acc_full[p]), 1);
                 mbar_init(smem_u32(&bars->acc_empty[p]), 2 * kEpiWarps);
             }
@@ -471,13 +512,13 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                                 const int atom = H == 256 ? sx : 2 * nc + sx;
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks) {
-                                    // H1 units 64 atom + 16ks .. +16: group g = 2 atom + ks/2, hi at column 32g + 8(ks%2), lo 16 further
-                                    const uint32_t ah = tm + (uint32_t)(32 * (2 * atom + (ks >> 1)) + 8 * (ks & 1));
+                                    // H1 units 64 atom + 16ks .. +16 = unit 4 atom + ks: hi at column 16 unit, lo 8 further
+                                    const uint32_t ah = tm + (uint32_t)(16 * (4 * atom + ks));
                                     const uint64_t bh = smem_desc_sw128(bbase) + (uint64_t)(ks * 2);
                                     mma2_f16_ts(d, ah, bh, idesc, (sx | ks) != 0);
                                     if (X3) {
                                         const uint64_t bl = smem_desc_sw128(bbase + 8192) + (uint64_t)(ks * 2);
-                                        mma2_f16_ts(d, ah + 16, bh, idesc, 1);      // H1_lo W_hi
+                                        mma2_f16_ts(d, ah + 8, bh, idesc, 1);       // H1_lo W_hi
                                         mma2_f16_ts(d, ah, bl, idesc, 1);           // H1_hi W_lo
                                     }
                                 }
@@ -490,12 +531,12 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                                     const int atom = 2 * nc + g2;
 #pragma unroll
                                     for (int ks = 0; ks < 4; ++ks) {
-                                        const uint32_t ah = tm + (uint32_t)(32 * (2 * atom + (ks >> 1)) + 8 * (ks & 1));
+                                        const uint32_t ah = tm + (uint32_t)(16 * (4 * atom + ks));
                                         const uint64_t bh = smem_desc_sw128(bbase + g2 * 4096) + (uint64_t)(ks * 2);
                                         mma2_f16_ts(d + 64 * g2, ah, bh, idesc64, ks != 0);
                                         if (X3) {
                                             const uint64_t bl = smem_desc_sw128(bbase + 8192 + g2 * 4096) + (uint64_t)(ks * 2);
-                                            mma2_f16_ts(d + 64 * g2, ah + 16, bh, idesc64, 1);
+                                            mma2_f16_ts(d + 64 * g2, ah + 8, bh, idesc64, 1);
                                             mma2_f16_ts(d + 64 * g2, ah, bl, idesc64, 1);
                                         }
                                     }
@@ -541,7 +582,7 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
         const uint32_t s1_addr = smem_u32(small1), s2_addr = smem_u32(small2);
         uint32_t acc_u = 0;
 
-        // ---------------- E1: H1 = tanh(D1 + b1') -> fp16 (hi [, lo]) written back IN PLACE
+        // ---------------- E1: H1 = tanh(D1 + b1') -> fp16 hi / lo written back IN PLACE, unit by unit (see e1_unit)
         auto epilogue1 = [&](uint32_t mi) {
             const uint32_t p = mi & 1;
             mbar_wait(BAR(s1_full, p), (mi >> 1) & 1);
@@ -551,41 +592,21 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                 mbar_wait(BAR(d1_full, nc), mi & 1);
                 tc_fence_after();
                 if (ew == 0 && lane == 0) TRACE(1, (int64_t)mi, 1 + 2 * nc);
+                const int u0 = 8 * nc + kEpiUnits * par;                  // this warp's units of the chunk: u0 .. u0 + kEpiUnits - 1
                 uint32_t va[16], vb[16];
-                tmem_ld16(tbase + 32 * (nc * 4 + par), va);
-                tmem_ld16(tbase + 32 * (nc * 4 + par) + 16, vb);
+                if (kEpiUnits > 0) tmem_ld16(tbase + 16 * u0, va);
+                if (kEpiUnits > 1) tmem_ld16(tbase + 16 * (u0 + 1), vb);
 #pragma unroll
-                for (int gi = 0; gi < 2; ++gi) {
-                    const int g = nc * 4 + gi * 2 + par;                  // 32-column group
-                    tmem_wait_ld16(va);                                   // both halves of the group are in registers:
-                    tmem_wait_ld16(vb);                                   // its columns may be overwritten
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint32_t *v = hf ? vb : va;
-                            const float4 b = lds128(b1 + (32 * g + 16 * hf + 4 * i) * 4);
-                            const float2 v01 = make_float2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]));
-                            const float2 v23 = make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-                            if (X3) {
-                                float2 t01, t23;
-                                tanh4(v01, v23, b, t01, t23);
-                                split_h2p(t01, hi[8 * hf + 2 * i], lo[8 * hf + 2 * i]);
-                                split_h2p(t23, hi[8 * hf + 2 * i + 1], lo[8 * hf + 2 * i + 1]);
-                            } else {
-                                const float2 x01 = fadd2(v01, make_float2(b.x, b.y)), x23 = fadd2(v23, make_float2(b.z, b.w));
-                                hi[8 * hf + 2 * i] = pack_h2(tanh_fast(x01.x), tanh_fast(x01.y));
-                                hi[8 * hf + 2 * i + 1] = pack_h2(tanh_fast(x23.x), tanh_fast(x23.y));
-                            }
-                        }
-                        // the next group of this chunk (other columns) streams in while this one is computed
-                        if (gi == 0) tmem_ld16(tbase + 32 * (g + 2) + 16 * hf, hf ? vb : va);
+                for (int j = 0; j < kEpiUnits; ++j) {
+                    if ((j & 1) == 0) {                // one wait covers both outstanding loads (units j and j + 1)
+                        tmem_wait_ld16(va);
+                        if (j + 1 < kEpiUnits) tmem_wait_ld16(vb);
                     }
-                    tmem_st16(tbase + 32 * g, hi);
-                    if (X3) tmem_st16(tbase + 32 * g + 16, lo);
+                    e1_unit<X3>(tbase + 16 * (u0 + j), b1 + (uint32_t)(16 * (u0 + j) * 4), (j & 1) ? vb : va);
+                    // the unit after next streams in (into the registers just consumed) while the next one is computed
+                    if (j + 2 < kEpiUnits) tmem_ld16(tbase + 16 * (u0 + j + 2), (j & 1) ? vb : va);
                 }
-                tmem_wait_st();                       // this chunk of H1 is complete: its k-atoms may be consumed
+                tmem_wait_st();                       // this warp's units of the chunk are complete
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) arrive_leader(BAR(h_ready, nc));
@@ -742,6 +763,35 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
             mbar_wait(bar, parity);
 #endif
         };
+        // This warp's share of the layer-1 epilogue of member `mt` (H < 256, see DES_PAIR_GEN_E1).  Everything it waits for
+        // precedes it in every generator warp's program order (the layer-1 tiles and b1' of mt, every slot of mt - 1) or is
+        // produced by the MMA / epilogue warps from such things: no cycle.
+        auto gen_e1 = [&](uint32_t mt, int nc) {
+            if constexpr (GE != 0) {
+                const int gi = warp >> 2;                                  // 0..3; TMEM lane quadrant = warp & 3
+                if (GE >= 4 || (gi >> 1) == nc) {
+                    const uint32_t pp = mt & 1;
+                    mbar_wait(BAR(s1_full, pp), (mt >> 1) & 1);           // b1' of that member (other generator warps wrote it)
+                    mbar_wait(BAR(d1_full, nc), mt & 1);
+                    tc_fence_after();
+                    constexpr int UW = GE == 8 ? 2 : 1;                   // units of a chunk per participating warp
+#pragma unroll
+                    for (int j = 0; j < UW; ++j) {
+                        // the epilogue warps own units 0 .. 7 - GE of the chunk, the generator warps the rest
+                        const uint32_t u = (uint32_t)(8 * nc + (GE == 8 ? 2 * gi + j : (GE == 4 ? 4 + gi : 6 + (gi & 1))));
+                        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 16 * u;
+                        uint32_t v[16];
+                        tmem_ld16(taddr, v);
+                        tmem_wait_ld16(v);
+                        e1_unit<X3>(taddr, smem_u32(small1) + pp * (uint32_t)(HH * 4) + 64 * u, v);
+                    }
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) arrive_leader(BAR(h_ready, nc));
+                }
+            }
+        };
         const int r2 = gtid >> 3, c82 = gtid & 7;
         const uint32_t ring_s = smem_u32(ring);                           // 32-bit shared addresses: STS, one register
         uint32_t oct_off[kOct];                                          // this thread's swizzled byte offsets inside a layer-2 tile
@@ -822,6 +872,9 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
                 if (lane == 0) arrive_leader(BAR(slot_full, s));
                 if (gtid == 0) TRACE(2, i, 1 + nc);
             }
+            // ---- H < 256: this warp's units of the layer-1 epilogue of THIS member, as soon as its layer-1 MMA has completed
+            gen_e1(mi, 0);
+            gen_e1(mi, 1);
             // ---- layer-2 tiles (the diagonal blocks only): 64 rows x 64 k per CTA and slot, one octet per thread.
             //      H = 256: rows [128nc + 64 rank, +64) of W2', k atom sx;  H = 128: member nc, rows [64 rank, +64), atom sx;
             //      H = 64: rows 0-31 of the slot = member 2nc, rows 32-63 = member 2nc+1, each rows [32 rank, +32) of its W2'
