@@ -321,7 +321,7 @@ def run_ours(a):
         def eval_only():
             eng.k.nes_eval(eng.theta, eng.obs, eng.target, hidden=H, sigma=eng.sigma, clip=eng.clip, seed=eng.seed,
                            state=eng.state, member_offset=eng.offset, n_local=eng.n_local, precision=eng.precision,
-                           out=eng.fitness_all[eng.offset:eng.offset + eng.n_local], workspace=eng.eval_ws)
+                           out=eng.fitness_shard_out, workspace=eng.eval_ws)
         for _ in range(2):
             eval_only()
         # The kernel is timed INSIDE eager generations (events around the launch, the rest of the generation behind it): the

@@ -80,7 +80,12 @@ class NESEngine:
             if int(ok.item()) == 0 and self.comm is not None:
                 self.comm.close()
                 self.comm = None
-        self.fitness_all = self.comm.fitness_all if self.comm is not None else torch.zeros(self.N, dtype=torch.float32, device=dev)
+        # fitness_all is PRIVATE to this rank: what callers read after generation().  With the peer-memory exchange the shard
+        # is evaluated into the exchange block (which every peer writes its own range of — a peer that runs ahead may already
+        # store the NEXT generation's shard there while this rank's host still reads this one) and the gathered vector is
+        # copied out of it, stream-ordered, before any peer can get that far.
+        self.fitness_all = torch.zeros(self.N, dtype=torch.float32, device=dev)
+        self._fitness_xchg = self.comm.fitness_all if self.comm is not None else self.fitness_all
         self.partial_local = torch.zeros(self.P, dtype=torch.float32, device=dev) if self.comm is not None else None
         self.shaped = torch.zeros(max(self.n_local, 1), dtype=torch.float32, device=dev)[:self.n_local]
         self.partial = torch.zeros(self.P, dtype=torch.float32, device=dev)
@@ -137,15 +142,21 @@ class NESEngine:
         if self.n_local:
             self.k.nes_eval(self.theta, self.obs, self.target, hidden=self.H, sigma=self.sigma, clip=self.clip,
                             seed=self.seed, state=self.state, member_offset=self.offset, n_local=self.n_local,
-                            precision=self.precision, out=self.fitness_all[self.offset:self.offset + self.n_local],
+                            precision=self.precision, out=self.fitness_shard_out,
                             workspace=self.eval_ws)
         self._gather_fitness()
         return self.fitness_all
 
+    @property
+    def fitness_shard_out(self):
+        """Where this rank's evaluation kernel writes its shard (the exchange block when peers read it from there)."""
+        return self._fitness_xchg[self.offset:self.offset + self.n_local]
+
     def _gather_fitness(self):
         if self.world > 1:
             if self.comm is not None:
-                self.comm.allgather_fitness(self.offset, self.n_local)     # shard -> every peer's fitness_all, flag barrier
+                self.comm.allgather_fitness(self.offset, self.n_local)     # shard -> every peer's exchange block, flag barrier
+                self.fitness_all.copy_(self._fitness_xchg)                 # the stable private copy (a 4N-byte device copy)
             else:
                 dist.all_reduce(self.fitness_all, group=self.pg)
 
@@ -295,7 +306,7 @@ class RolloutEngine(NESEngine):
                                 member_offset=self.offset, n_local=self.n_local,
                                 obs_stats=self.obs_stats if self.normalize_obs else None,
                                 totals_out=self.obs_totals if self.normalize_obs else None, workspace=self.roll_ws,
-                                out=self.fitness_all[self.offset:self.offset + self.n_local])
+                                out=self.fitness_shard_out)
         self._gather_fitness()
         if self.world > 1 and self.normalize_obs:
             dist.all_reduce(self.obs_totals, group=self.pg)
