@@ -255,7 +255,9 @@ DES_API int des_cma_rank_mu_tc(float *out_dev, const float *Y_dev, const float *
  *   des_comm_create     allocates the local block on the current device; ipc_handle_out receives 64 bytes to hand to
  *                       every peer (any transport: torch.distributed all_gather, a file, MPI ...)
  *   des_comm_connect    all_handles = world x 64 bytes in rank order; maps the peers' blocks (enables P2P access)
- *   des_comm_fitness_all_dev   the local fitness_all[N]: des_nes_eval writes the shard here
+ *   des_comm_fitness_all_dev   the local fitness_all[N]: des_nes_eval writes the shard here.  Peers store into it: a host
+ *                       that reads it after a generation must take a stream-ordered copy right after the all-gather
+ *                       (a peer that runs ahead may already be storing its next shard)
  *   des_comm_allgather_fitness stores the local shard [member_offset, +n_local) into every peer's fitness_all and
  *                       returns (on the stream) when every peer's shard has landed here: all ranks then hold the same N values
  *   des_comm_allreduce_partial  partial_sum_out[j] = sum over ranks r = 0..world-1, in that order, of rank r's
