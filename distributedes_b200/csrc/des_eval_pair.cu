@@ -326,6 +326,7 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
     using C = Cfg<H, X3>;
     constexpr int GE = GenE1<H>::value;               // units per chunk taken by the generator warps of a quadrant
     constexpr int kEpiUnits = (8 - GE) / 2;           // ... and by each of the two epilogue warps
+    static_assert(GE == 0 || kGenWarps == 16, "the unit assignment of the generator warps assumes four of them per lane quadrant");
     const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
