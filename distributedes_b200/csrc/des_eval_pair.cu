@@ -35,7 +35,7 @@
 //
 // Warp roles (warpgroup-aligned for setmaxnreg): warps 0-15 weight generators, warp 16 TMEM allocator + MMA issuer (leader
 // CTA only), warp 17 TMA producer of the theta boxes, warps 18-19 idle, warps 20-27 epilogue (two per TMEM lane
-// quadrant = warp id % 4, alternating 32-column groups).
+// quadrant = warp id % 4: consecutive 16-column units of a chunk in layer 1, alternating 32-column groups in layer 2).
 #include <cuda.h>
 #include <stddef.h>
 #include <stdlib.h>
@@ -576,7 +576,7 @@ __global__ void __maxnreg__(kLaunchRegs) eval_pair_kernel(Args a, const __grid_c
         // =================================== epilogue warps ============================================
         reg_alloc<kEpiRegs>();
         const int ew = warp - kEpiWarp0;                              // 0..7; TMEM lane quadrant = warp id % 4 = ew % 4
-        const int par = ew >> 2;                                      // this warp owns the 32-column groups g with (g & 1) == par
+        const int par = ew >> 2;                                      // layer 1: units kEpiUnits*par ..; layer 2: the 32-column groups g with (g & 1) == par
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
         const int row = (warp & 3) * 32 + lane;                       // observation row inside this CTA's tile
         const uint32_t tbase = tmem + lane_off;
